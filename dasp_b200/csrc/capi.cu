@@ -1,0 +1,280 @@
+// capi.cu — the C ABI of include/dasp.h on top of preprocess.cu / spmv.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "dasp_internal.h"
+
+namespace dasp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevicePool::alloc(void **p, size_t n)
+{
+    *p = nullptr;
+    size_t want = n ? n : 256; // zero-length arrays still get a valid, aligned pointer
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) -> %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? DASP_ERR_ALLOC : DASP_ERR_CUDA;
+    }
+    ptrs.push_back(*p);
+    bytes += (int64_t)want;
+    return DASP_OK;
+}
+
+void DevicePool::release(void *p)
+{
+    auto it = std::find(ptrs.begin(), ptrs.end(), p);
+    if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); }
+}
+
+void DevicePool::free_all()
+{
+    for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// bring one CSR array to the device if it is a host pointer
+static int stage(DevicePool &tmp, const void *src, size_t bytes, const void **dst, cudaStream_t st)
+{
+    if (bytes == 0 || is_device_ptr(src)) { *dst = src; return DASP_OK; }
+    void *d = nullptr;
+    DASP_TRY(tmp.alloc(&d, bytes));
+    DASP_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+    *dst = d;
+    return DASP_OK;
+}
+
+} // namespace dasp
+
+using namespace dasp;
+
+extern "C" {
+
+const char *dasp_strerror(int status)
+{
+    switch (status) {
+    case DASP_OK: return "ok";
+    case DASP_ERR_INVALID: return "invalid argument";
+    case DASP_ERR_CUDA: return "CUDA error";
+    case DASP_ERR_ALLOC: return "allocation failed";
+    case DASP_ERR_RANGE: return "size exceeds the 32-bit layout";
+    case DASP_ERR_BUFFER: return "destination buffer too small";
+    default: return "unknown status";
+    }
+}
+
+const char *dasp_last_error(void) { return g_err; }
+
+int dasp_create(dasp_handle **out, dasp_dtype dtype, int device, int m, int n, int64_t nnz, const int *rowptr,
+                const int *colidx, const void *val, double threshold, int block_longest)
+{
+    if (!out) { set_error("handle pointer is NULL"); return DASP_ERR_INVALID; }
+    *out = nullptr;
+    if (m < 0 || n < 0 || nnz < 0 || !rowptr || (nnz > 0 && (!colidx || !val)) || (dtype != DASP_F64 && dtype != DASP_F16) ||
+        !(threshold > 0.0) || block_longest < 1) {
+        set_error("dasp_create: bad argument (m=%d n=%d nnz=%lld threshold=%g block_longest=%d)", m, n, (long long)nnz,
+                  threshold, block_longest);
+        return DASP_ERR_INVALID;
+    }
+    if (nnz > INT32_MAX) { set_error("nnz=%lld does not fit the reference's 32-bit row pointers", (long long)nnz); return DASP_ERR_RANGE; }
+    DASP_CUDA(cudaSetDevice(device));
+    dasp_handle *h = new (std::nothrow) dasp_handle();
+    if (!h) { set_error("out of host memory"); return DASP_ERR_ALLOC; }
+    h->device = device; h->dtype = dtype; h->threshold = threshold; h->block_longest = block_longest;
+
+    int rc = DASP_OK;
+    DevicePool staging;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if ((rc = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess ? DASP_OK : DASP_ERR_CUDA)) {
+            set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaStream_t st = h->own_stream;
+        const size_t esz = dtype == DASP_F16 ? 2 : 8;
+        const void *d_rowptr = nullptr, *d_colidx = nullptr, *d_val = nullptr;
+        if ((rc = stage(staging, rowptr, sizeof(int) * ((size_t)m + 1), &d_rowptr, st))) break;
+        if ((rc = stage(staging, colidx, sizeof(int) * (size_t)nnz, &d_colidx, st))) break;
+        if ((rc = stage(staging, val, esz * (size_t)nnz, &d_val, st))) break;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        if ((rc = preprocess(h, m, n, nnz, (const int *)d_rowptr, (const int *)d_colidx, d_val, st))) break;
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("preprocessing failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DASP_ERR_CUDA; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        h->L.s.preprocess_ms = ms;
+        h->L.s.device_bytes = h->pool.bytes;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    staging.free_all();
+    if (rc != DASP_OK) { dasp_destroy(h); return rc; }
+    *out = h;
+    return DASP_OK;
+}
+
+int dasp_destroy(dasp_handle *h)
+{
+    if (!h) return DASP_OK;
+    cudaSetDevice(h->device);
+    h->pool.free_all();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DASP_OK;
+}
+
+int dasp_spmv(dasp_handle *h, const void *d_x, void *d_y, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv: NULL argument"); return DASP_ERR_INVALID; }
+    return launch_spmv(h, d_x, d_y, nullptr, (cudaStream_t)stream);
+}
+
+int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_unpermuted: NULL argument"); return DASP_ERR_INVALID; }
+    return launch_spmv(h, d_x, d_y, h->L.order_rid, (cudaStream_t)stream);
+}
+
+int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host)
+{
+    if (!h || (!x_host && h->L.s.n > 0) || (!y_host && h->L.s.m > 0)) { set_error("dasp_spmv_host: NULL argument"); return DASP_ERR_INVALID; }
+    DASP_CUDA(cudaSetDevice(h->device));
+    const size_t esz = h->dtype == DASP_F16 ? 2 : 8;
+    const size_t xb = esz * (size_t)h->L.s.n, yb = esz * (size_t)h->L.s.m;
+    if (!h->dx_stage) { // device-side staging buffers, allocated once
+        DASP_TRY(h->pool.alloc(&h->dx_stage, xb));
+        DASP_TRY(h->pool.alloc(&h->dy_stage, yb));
+    }
+    cudaStream_t st = h->own_stream;
+    DASP_CUDA(cudaMemcpyAsync(h->dx_stage, x_host, xb, cudaMemcpyHostToDevice, st));
+    DASP_TRY(launch_spmv(h, h->dx_stage, h->dy_stage, nullptr, st));
+    DASP_CUDA(cudaMemcpyAsync(y_host, h->dy_stage, yb, cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    return DASP_OK;
+}
+
+int dasp_order(const dasp_handle *h, const int **d_order_rid)
+{
+    if (!h || !d_order_rid) { set_error("dasp_order: NULL argument"); return DASP_ERR_INVALID; }
+    *d_order_rid = h->L.order_rid;
+    return DASP_OK;
+}
+
+int dasp_stats(const dasp_handle *h, dasp_stats_t *out)
+{
+    if (!h || !out) { set_error("dasp_stats: NULL argument"); return DASP_ERR_INVALID; }
+    *out = h->L.s;
+    return DASP_OK;
+}
+
+int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes, int64_t *bytes)
+{
+    if (!h || !name) { set_error("dasp_export: NULL argument"); return DASP_ERR_INVALID; }
+    const Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    const int64_t ev = (int64_t)L.esz, ei = sizeof(int);
+    struct Entry { const char *name; const void *ptr; int64_t bytes; };
+    const Entry table[] = {
+        {"order_rid", L.order_rid, ei * s.m},
+        {"long_rpt_new", L.long_rpt_new, ei * ((int64_t)s.row_long + 1)},
+        {"long_val", L.long_val, ev * s.fill0_nnz_long},
+        {"long_cid", L.long_cid, ei * s.fill0_nnz_long},
+        {"blockPtr", L.blockPtr, ei * ((int64_t)s.blocknum + 1)},
+        {"irreg_rpt", L.irreg_rpt, ei * ((int64_t)s.row_block + 1)},
+        {"irreg_val", L.irreg_val, ev * s.fill0_nnz_irreg},
+        {"irreg_cid", L.irreg_cid, ei * s.nnz_irreg},
+        {"reg_val", L.reg_val, ev * s.fill0_nnz_reg},
+        {"reg_cid", L.reg_cid, ei * s.fill0_nnz_reg},
+        {"short_val", L.short_val, ev * s.fill0_nnz_short},
+        {"short_cid", L.short_cid, ei * s.fill0_nnz_short},
+    };
+    for (const Entry &e : table) {
+        if (strcmp(e.name, name)) continue;
+        if (bytes) *bytes = e.bytes;
+        if (!host_dst) return DASP_OK;
+        if (cap_bytes < e.bytes) { set_error("dasp_export(%s): need %lld bytes, got %lld", name, (long long)e.bytes, (long long)cap_bytes); return DASP_ERR_BUFFER; }
+        DASP_CUDA(cudaSetDevice(h->device));
+        if (e.bytes > 0) DASP_CUDA(cudaMemcpy(host_dst, e.ptr, (size_t)e.bytes, cudaMemcpyDeviceToHost));
+        return DASP_OK;
+    }
+    set_error("dasp_export: unknown array '%s'", name);
+    return DASP_ERR_INVALID;
+}
+
+int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows)
+{
+    if (!h) { set_error("dasp_set_variant: NULL handle"); return DASP_ERR_INVALID; }
+    h->var_medium = medium; h->var_long = long_rows; h->var_short = short_rows;
+    return DASP_OK;
+}
+
+int dasp_launches_per_spmv(const dasp_handle *h) { return h ? launches_per_spmv(h) : 0; }
+
+static int spmv_all_impl(dasp_dtype dt, const void *val, const int *rowptr, const int *colidx, const void *x, void *y,
+                         int *order_rid, int m, int n, int nnz, double threshold, int block_longest)
+{
+    dasp_handle *h = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return DASP_ERR_CUDA; }
+    DASP_TRY(dasp_create(&h, dt, dev, m, n, nnz, rowptr, colidx, val, threshold, block_longest));
+    int rc = dasp_spmv_host(h, x, y);
+    if (rc == DASP_OK && order_rid) rc = dasp_export(h, "order_rid", order_rid, (int64_t)sizeof(int) * m, nullptr);
+    dasp_destroy(h);
+    return rc;
+}
+
+int dasp_spmv_all_f64(const char *, const double *csrValA, const int *csrRowPtrA, const int *csrColIdxA, const double *X_val,
+                      double *Y_val, int *order_rid, int rowA, int colA, int nnzA, int, double threshold, int block_longest)
+{
+    return spmv_all_impl(DASP_F64, csrValA, csrRowPtrA, csrColIdxA, X_val, Y_val, order_rid, rowA, colA, nnzA, threshold,
+                         block_longest);
+}
+
+int dasp_spmv_all_f16(const char *, const void *csrValA, const int *csrRowPtrA, const int *csrColIdxA, const void *X_val,
+                      void *Y_val, int *order_rid, int rowA, int colA, int nnzA, int, double threshold, int block_longest)
+{
+    return spmv_all_impl(DASP_F16, csrValA, csrRowPtrA, csrColIdxA, X_val, Y_val, order_rid, rowA, colA, nnzA, threshold,
+                         block_longest);
+}
+
+int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts)
+{
+    if (m < 0 || !rowptr || parts < 1 || !cuts) { set_error("dasp_partition_rows: bad argument"); return DASP_ERR_INVALID; }
+    const int64_t nnz = rowptr[m] - (int64_t)rowptr[0];
+    cuts[0] = 0;
+    for (int p = 1; p < parts; p++) {
+        const int64_t target = rowptr[0] + nnz * p / parts;
+        const int *it = std::lower_bound(rowptr + cuts[p - 1], rowptr + m + 1, target,
+                                         [](int v, int64_t t) { return (int64_t)v < t; });
+        int c = (int)(it - rowptr);
+        cuts[p] = c > m ? m : c;
+    }
+    cuts[parts] = m;
+    return DASP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,94 @@
+// dasp_internal.h — handle layout and helpers shared by the translation units of libdasp_b200.so
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dasp.h"
+
+namespace dasp {
+
+void set_error(const char *fmt, ...);
+
+#define DASP_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ::dasp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorMemoryAllocation) ? DASP_ERR_ALLOC : DASP_ERR_CUDA;           \
+        }                                                                                        \
+    } while (0)
+
+#define DASP_TRY(expr)                   \
+    do {                                 \
+        int s_ = (expr);                 \
+        if (s_ != DASP_OK) return s_;    \
+    } while (0)
+
+// Tracks every device allocation of a handle so destroy/fail paths free them all.
+struct DevicePool {
+    std::vector<void *> ptrs;
+    int64_t bytes = 0;
+    int alloc(void **p, size_t n);
+    void release(void *p);
+    void free_all();
+};
+
+// Work list entry of the long-row kernel: one warp reduces elements [begin, end) of long row `row`.
+struct LongUnit {
+    int row;
+    int slot; // index into the partial-sum scratch (== unit id)
+    int begin, end;
+};
+
+struct Layout {
+    dasp_stats_t s{};
+    size_t esz = 8;
+    // ---- the reference's arrays (bit-exact) ----
+    int *order_rid = nullptr;
+    int *long_rpt_new = nullptr;
+    void *long_val = nullptr;
+    int *long_cid = nullptr;
+    int *blockPtr = nullptr;
+    int *irreg_rpt = nullptr;
+    void *irreg_val = nullptr;
+    int *irreg_cid = nullptr;
+    void *reg_val = nullptr;
+    int *reg_cid = nullptr;
+    void *short_val = nullptr;
+    int *short_cid = nullptr;
+    // ---- derived launch data of this implementation (not part of the reference layout) ----
+    int n_long_units = 0;
+    int *long_unit_row = nullptr;   // [n_long_units] long row of each unit
+    int *long_unit_first = nullptr; // [row_long+1]  first unit of each long row
+    void *long_partial = nullptr;   // [n_long_units] double (f64) / float (f16) partial sums
+    unsigned *long_done = nullptr;  // [row_long] arrival counters (self-resetting)
+    unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
+};
+
+} // namespace dasp
+
+struct dasp_handle {
+    int device = 0;
+    dasp_dtype dtype = DASP_F64;
+    double threshold = 0.75;
+    int block_longest = 256;
+    dasp::Layout L;
+    dasp::DevicePool pool;
+    dasp_variant var_medium = DASP_VARIANT_AUTO, var_long = DASP_VARIANT_AUTO, var_short = DASP_VARIANT_AUTO;
+    // device staging of x / y for dasp_spmv_host (owned by pool)
+    void *dx_stage = nullptr, *dy_stage = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace dasp {
+// preprocess.cu
+int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx,
+               const void *d_val, cudaStream_t st);
+// spmv.cu
+int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st);
+int launches_per_spmv(const dasp_handle *h);
+} // namespace dasp

@@ -1,0 +1,501 @@
+// spmv.cu — y = A*x on the DASP layout, hand-written for sm_100a.
+//
+// Replaces the reference kernels dasp_spmv2<rowloop> + longPart_sum (src/dasp_f64.h:53-484,
+// src/dasp_f16.h:106-590).  One fused launch; the block index selects the row category like the
+// reference does (src/dasp_f64.h:90,145,281,296,357,424), but the geometry is this implementation's:
+//
+//   long    one warp per work unit (<= 32 reference warps = 2048/8192 slots of ONE row); 128-bit value
+//           and 64-bit index loads; a row that spans several units is merged deterministically by the
+//           last unit to arrive (self-resetting counter) — no second launch (K1+K2 of SURVEY §8a).
+//   medium  one warp per 4 blocks of 8 rows; lane = (block, row).  CUDA-core variant: every lane walks
+//           the 8x4 tiles of its row with one 256-bit value load + one 128-bit index load per tile and
+//           keeps its own accumulator (no cross-lane traffic, same summation order as serial CSR).
+//           MMA variant: the reference's DMMA m8n8k4 formulation on the same tiles (K3).
+//   short   1 / 1&3 / 3&4 / 2&2 segments read as flat coalesced streams (alignment-free: the FP64
+//           short segments start at slot short_row_1, which is not a multiple of 4) and folded with
+//           shuffles inside each 4-slot tile row (K4-K7).
+//   zero    rows without entries are written as 0 every call (the reference relies on a one-time
+//           cudaMemset, src/dasp_f64.h:1242).
+//
+// y is produced in permuted order (K11); with `scatter` (= order_rid) it is written to original order.
+#include <cuda_fp16.h>
+
+#include "dasp_internal.h"
+
+namespace dasp {
+namespace {
+
+constexpr int CTA = 256;
+constexpr int WARPS = CTA / 32;
+constexpr int LONG_UNIT_WARPS = 32; // must match preprocess.cu
+constexpr int SINGLES_PER_THREAD = 4;
+constexpr int SHORT_TILES_PER_WARP = 4;
+
+struct SpmvArgs {
+    const void *x;
+    void *y;
+    const int *scatter; // nullptr: permuted order
+    // long
+    const void *long_val;
+    const int *long_cid, *long_rpt_new, *unit_row, *unit_first;
+    void *partial;
+    unsigned *done;
+    int n_units, longw;
+    // medium
+    const void *reg_val;
+    const int *reg_cid, *blockPtr, *irreg_rpt;
+    const void *irreg_val;
+    const int *irreg_cid;
+    const unsigned char *has_irreg;
+    int row_long, row_block, blocknum;
+    // short
+    const void *short_val;
+    const int *short_cid;
+    int n1, c13, n34, n2;
+    int s1, s13, s34, s22;     // slot bases
+    int y1, y13, y34, y22, y0; // y bases (K11)
+    int G;                     // 8 (f64) / 32 (f16)
+    int row_zero;
+    // exclusive block-range ends
+    int e_long, e_med, e_s1, e_s13, e_s34, e_s22, e_zero;
+};
+
+template <typename T> struct Acc;
+template <> struct Acc<double> { using type = double; };
+template <> struct Acc<__half> { using type = float; };
+
+__device__ __forceinline__ double to_acc(double v) { return v; }
+__device__ __forceinline__ float to_acc(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_acc(double *p, double v) { *p = v; }
+__device__ __forceinline__ void from_acc(__half *p, float v) { *p = __float2half_rn(v); }
+
+// ---- streaming loads of the packed matrix: read once, so keep them out of L1 and mark them evict-first in
+// L2 (x must survive there).  Only the 256-bit form takes .L2::evict_first directly; narrower loads go
+// through a createpolicy descriptor.
+__device__ __forceinline__ uint64_t make_stream_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define DASP_LD_HINT "ld.global.nc.L1::no_allocate.L2::cache_hint"
+__device__ __forceinline__ void ld_stream4(const double *p, double (&v)[4], uint64_t)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream4(const __half *p, __half (&v)[4], uint64_t pol)
+{
+    unsigned a, b;
+    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol));
+    __half2 h0 = *reinterpret_cast<__half2 *>(&a), h1 = *reinterpret_cast<__half2 *>(&b);
+    v[0] = __low2half(h0); v[1] = __high2half(h0); v[2] = __low2half(h1); v[3] = __high2half(h1);
+}
+__device__ __forceinline__ void ld_stream4(const int *p, int (&v)[4], uint64_t pol)
+{
+    asm volatile(DASP_LD_HINT ".v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_stream2(const double *p, double (&v)[2], uint64_t pol)
+{
+    asm volatile(DASP_LD_HINT ".v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_stream2(const __half *p, __half (&v)[2], uint64_t pol)
+{
+    unsigned a;
+    asm volatile(DASP_LD_HINT ".u32 %0, [%1], %2;" : "=r"(a) : "l"(p), "l"(pol));
+    __half2 h = *reinterpret_cast<__half2 *>(&a);
+    v[0] = __low2half(h); v[1] = __high2half(h);
+}
+__device__ __forceinline__ void ld_stream2(const int *p, int (&v)[2], uint64_t pol)
+{
+    asm volatile(DASP_LD_HINT ".v2.s32 {%0,%1}, [%2], %3;" : "=r"(v[0]), "=r"(v[1]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ double ld_stream1(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile(DASP_LD_HINT ".f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ __half ld_stream1(const __half *p, uint64_t pol)
+{
+    unsigned short v;
+    asm volatile(DASP_LD_HINT ".u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return __ushort_as_half(v);
+}
+__device__ __forceinline__ int ld_stream1(const int *p, uint64_t pol)
+{
+    int v;
+    asm volatile(DASP_LD_HINT ".s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// x gathers: read-only path, allocate in L1 (neighbouring rows reuse the same entries)
+template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c) { return to_acc(__ldg(x + c)); }
+
+template <typename T>
+__device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Acc<T>::type v)
+{
+    T *y = static_cast<T *>(a.y);
+    if (a.scatter) idx = a.scatter[idx];
+    from_acc(y + idx, v);
+}
+
+template <typename A> __device__ __forceinline__ A warp_sum(A v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// long rows
+
+template <typename T, bool MMA>
+__device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
+{
+    const uint64_t pol = make_stream_policy();
+    using A = typename Acc<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int u = cta * WARPS + (threadIdx.x >> 5);
+    if (u >= a.n_units) return;
+    const T *x = static_cast<const T *>(a.x);
+    const int row = __ldg(a.unit_row + u);
+    const int first = __ldg(a.unit_first + row), nunits = __ldg(a.unit_first + row + 1) - first;
+    const long row_beg = (long)__ldg(a.long_rpt_new + row) * a.longw, row_end = (long)__ldg(a.long_rpt_new + row + 1) * a.longw;
+    const long beg = row_beg + (long)(u - first) * LONG_UNIT_WARPS * a.longw;
+    const long end = min(beg + (long)LONG_UNIT_WARPS * a.longw, row_end);
+    const T *val = static_cast<const T *>(a.long_val);
+    A acc = 0;
+    if constexpr (MMA && sizeof(T) == 8) {
+        // the reference's formulation (src/dasp_f64.h:105-122): 32 slots per DMMA, the useful products sit on
+        // the diagonal of C; everything in C is summed, off-diagonal terms are masked out by zeroing B.
+        double c[2] = {0.0, 0.0};
+        const int grp = lane >> 2;
+        for (long p = beg + lane; p < end; p += 128) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                long q = p + 32 * j;
+                bool ok = q < end;
+                av[j] = ok ? (double)ld_stream1(reinterpret_cast<const double *>(val) + q, pol) : 0.0;
+                int cid = ok ? ld_stream1(a.long_cid + q, pol) : 0;
+                bv[j] = ok ? (double)gather(reinterpret_cast<const double *>(x), cid) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(c, av[j], bv[j]);
+        }
+        // C[g][n]: lane holds row g = lane>>2, columns 2*(lane&3)+{0,1}; keep only n == g
+        const int n0 = 2 * (lane & 3);
+        double d = (n0 == grp ? c[0] : 0.0) + (n0 + 1 == grp ? c[1] : 0.0);
+        acc = (A)warp_sum(d);
+    } else {
+        A s0 = 0, s1 = 0;
+        // 64 slots per warp step (2 per lane); units are multiples of 64 slots
+        long p = beg + 2 * lane;
+        for (; p + 192 < end; p += 256) {
+            T v[4][2];
+            int c[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { ld_stream2(val + p + 64 * j, v[j], pol); ld_stream2(a.long_cid + p + 64 * j, c[j], pol); }
+            A g[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { g[j][0] = gather(x, c[j][0]); g[j][1] = gather(x, c[j][1]); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { s0 += to_acc(v[j][0]) * g[j][0]; s1 += to_acc(v[j][1]) * g[j][1]; }
+        }
+        for (; p < end; p += 64) {
+            T v[2];
+            int c[2];
+            ld_stream2(val + p, v, pol);
+            ld_stream2(a.long_cid + p, c, pol);
+            s0 += to_acc(v[0]) * gather(x, c[0]);
+            s1 += to_acc(v[1]) * gather(x, c[1]);
+        }
+        acc = warp_sum(s0 + s1);
+    }
+    if (nunits == 1) {
+        if (lane == 0) store_y<T>(a, row, acc);
+        return;
+    }
+    // multi-unit row: publish the partial, the last unit to arrive folds them in unit order (deterministic)
+    A *partial = static_cast<A *>(a.partial);
+    unsigned prev = 0;
+    if (lane == 0) {
+        __stcg(partial + u, acc);
+        __threadfence();
+        prev = atomicAdd(a.done + row, 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev != (unsigned)(nunits - 1)) return;
+    __threadfence();
+    A t = 0;
+    for (int i = lane; i < nunits; i += 32) t += __ldcg(partial + first + i);
+    t = warp_sum(t);
+    if (lane == 0) {
+        store_y<T>(a, row, t);
+        a.done[row] = 0; // ready for the next call
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// medium rows (row blocks)
+
+template <typename T, bool MMA>
+__device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
+{
+    const uint64_t pol = make_stream_policy();
+    using A = typename Acc<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int group = cta * WARPS + (threadIdx.x >> 5); // 32 rows = 4 blocks
+    if (group * 4 >= a.blocknum) return;
+    const T *x = static_cast<const T *>(a.x);
+    const T *val = static_cast<const T *>(a.reg_val);
+    const int g = group * 32 + lane;
+    A acc = 0;
+    if constexpr (MMA && sizeof(T) == 8) {
+        // DMMA m8n8k4 per 8x4 tile, one block after the other (src/dasp_f64.h:240-269 restated)
+        const double *dval = reinterpret_cast<const double *>(val);
+        const double *dx = reinterpret_cast<const double *>(x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int b = group * 4 + i;
+            const int bp0 = __ldg(a.blockPtr + b), bp1 = __ldg(a.blockPtr + b + 1);
+            double c[2] = {0.0, 0.0};
+            int p = bp0 + lane;
+            for (; p + 96 < bp1; p += 128) {
+                double av[4], bv[4];
+                int cid[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { av[j] = ld_stream1(dval + p + 32 * j, pol); cid[j] = ld_stream1(a.reg_cid + p + 32 * j, pol); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) bv[j] = __ldg(dx + cid[j]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(c, av[j], bv[j]);
+            }
+            for (; p < bp1; p += 32) {
+                double av = ld_stream1(dval + p, pol);
+                double bv = __ldg(dx + ld_stream1(a.reg_cid + p, pol));
+                dmma884(c, av, bv);
+            }
+            // C[r][r] sits in lane 4r + (r>>1), register r&1; route it to lane 8i + r
+            const int r = lane & 7, src = 4 * r + (r >> 1);
+            double v0 = __shfl_sync(0xffffffffu, c[0], src), v1 = __shfl_sync(0xffffffffu, c[1], src);
+            if ((lane >> 3) == i) acc = (A)((r & 1) ? v1 : v0);
+        }
+    } else {
+        const int b = g >> 3, r = g & 7;
+        const int bp0 = __ldg(a.blockPtr + b), bp1 = __ldg(a.blockPtr + b + 1);
+        const T *pv = val + bp0 + 4 * r;
+        const int *pc = a.reg_cid + bp0 + 4 * r;
+        const int nt = (bp1 - bp0) >> 5;
+        int k = 0;
+        for (; k + 4 <= nt; k += 4) {
+            T v[4][4];
+            int c[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { ld_stream4(pv + 32 * (k + j), v[j], pol); ld_stream4(pc + 32 * (k + j), c[j], pol); }
+            A xv[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+        }
+        for (; k < nt; k++) {
+            T v[4];
+            int c[4];
+            ld_stream4(pv + 32 * k, v, pol);
+            ld_stream4(pc + 32 * k, c, pol);
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc += to_acc(v[e]) * gather(x, c[e]);
+        }
+    }
+    if (g >= a.row_block) return;
+    if (a.has_irreg[group]) {
+        const T *iv = static_cast<const T *>(a.irreg_val);
+        const int lo = __ldg(a.irreg_rpt + g), hi = __ldg(a.irreg_rpt + g + 1);
+        for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
+    }
+    store_y<T>(a, (long)a.row_long + g, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// short rows
+
+template <typename T>
+__device__ __forceinline__ void short_singles(const SpmvArgs &a, int cta)
+{
+    const uint64_t pol = make_stream_policy();
+    const T *x = static_cast<const T *>(a.x);
+    const T *val = static_cast<const T *>(a.short_val) + a.s1;
+    const int *cid = a.short_cid + a.s1;
+    const long base = (long)cta * CTA * SINGLES_PER_THREAD + threadIdx.x;
+    T v[SINGLES_PER_THREAD];
+    int c[SINGLES_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < SINGLES_PER_THREAD; j++) {
+        long i = base + j * CTA;
+        if (i < a.n1) { v[j] = ld_stream1(val + i, pol); c[j] = ld_stream1(cid + i, pol); }
+    }
+#pragma unroll
+    for (int j = 0; j < SINGLES_PER_THREAD; j++) {
+        long i = base + j * CTA;
+        if (i < a.n1) store_y<T>(a, a.y1 + i, to_acc(v[j]) * gather(x, c[j]));
+    }
+}
+
+// y index of tile T (8 tile rows), row r, half h inside a 1&3 or 2&2 segment:
+// FP64 interleaves per tile (G = 8), FP16 per group of 4 tiles (G = 32); K11 / P10 of SURVEY §8a
+__device__ __forceinline__ long paired_y(int G, long tile, int r, int h)
+{
+    const int tg = G >> 3;
+    return (tile / tg) * (2L * G) + (long)h * G + (tile % tg) * 8 + r;
+}
+
+// MODE 0: 1&3 tiles   MODE 1: 3/4 rows   MODE 2: 2&2 tiles
+template <typename T, int MODE>
+__device__ __forceinline__ void short_tiles(const SpmvArgs &a, int cta)
+{
+    const uint64_t pol = make_stream_policy();
+    using A = typename Acc<T>::type;
+    const int lane = threadIdx.x & 31;
+    const T *x = static_cast<const T *>(a.x);
+    const int sbase = MODE == 0 ? a.s13 : (MODE == 1 ? a.s34 : a.s22);
+    const long nrows = MODE == 0 ? a.c13 : (MODE == 1 ? a.n34 : a.n2); // rows (pairs for MODE 0)
+    const T *val = static_cast<const T *>(a.short_val) + sbase;
+    const int *cid = a.short_cid + sbase;
+    const long tile0 = ((long)cta * WARPS + (threadIdx.x >> 5)) * SHORT_TILES_PER_WARP;
+    // 2&2 packs 2G rows per G/8 tiles (16 per tile in FP64, 64 per 4 tiles in FP16)
+    const long tiles_avail = MODE == 2 ? ((nrows + 2 * a.G - 1) / (2 * a.G)) * (a.G >> 3) : (nrows + 7) / 8;
+    A p[SHORT_TILES_PER_WARP];
+    T v[SHORT_TILES_PER_WARP];
+    int c[SHORT_TILES_PER_WARP];
+#pragma unroll
+    for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
+        bool ok = tile0 + j < tiles_avail;
+        long s = (tile0 + j) * 32 + lane;
+        v[j] = ok ? ld_stream1(val + s, pol) : T(0);
+        c[j] = ok ? ld_stream1(cid + s, pol) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
+    const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
+        const long tile = tile0 + j;
+        if (MODE == 1) {
+            A s = p[j] + __shfl_xor_sync(0xffffffffu, p[j], 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            long row = tile * 8 + r;
+            if (q == 0 && row < nrows) store_y<T>(a, a.y34 + row, s);
+        } else if (MODE == 0) {
+            A d1 = __shfl_down_sync(0xffffffffu, p[j], 1), d2 = __shfl_down_sync(0xffffffffu, p[j], 2);
+            long pair = tile * 8 + r;
+            if (pair < nrows) {
+                if (q == 0) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), p[j]);
+                if (q == 1) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), p[j] + d1 + d2);
+            }
+        } else {
+            A d1 = __shfl_down_sync(0xffffffffu, p[j], 1);
+            if ((q & 1) == 0) {
+                long yi = paired_y(a.G, tile, r, q >> 1);
+                if (yi < nrows) store_y<T>(a, a.y22 + yi, p[j] + d1);
+            }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void zero_rows(const SpmvArgs &a, int cta)
+{
+    long i = (long)cta * CTA + threadIdx.x;
+    if (i < a.row_zero) store_y<T>(a, a.y0 + i, typename Acc<T>::type(0));
+}
+
+template <typename T, bool MMA_MED, bool MMA_LONG>
+__global__ void __launch_bounds__(CTA) spmv_kernel(const __grid_constant__ SpmvArgs a)
+{
+    const int bid = blockIdx.x;
+    if (bid < a.e_long) long_rows<T, MMA_LONG>(a, bid);
+    else if (bid < a.e_med) medium_rows<T, MMA_MED>(a, bid - a.e_long);
+    else if (bid < a.e_s1) short_singles<T>(a, bid - a.e_med);
+    else if (bid < a.e_s13) short_tiles<T, 0>(a, bid - a.e_s1);
+    else if (bid < a.e_s34) short_tiles<T, 1>(a, bid - a.e_s13);
+    else if (bid < a.e_s22) short_tiles<T, 2>(a, bid - a.e_s34);
+    else zero_rows<T>(a, bid - a.e_s22);
+}
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+} // namespace
+
+int launches_per_spmv(const dasp_handle *) { return 1; }
+
+int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st)
+{
+    const Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    const bool f16 = h->dtype == DASP_F16;
+    SpmvArgs a{};
+    a.x = d_x; a.y = d_y; a.scatter = scatter;
+    a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
+    a.unit_row = L.long_unit_row; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
+    a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
+    a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
+    a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
+    a.row_long = s.row_long; a.row_block = s.row_block; a.blocknum = s.blocknum;
+    a.short_val = L.short_val; a.short_cid = L.short_cid;
+    a.n1 = s.short_row_1; a.c13 = s.common_13; a.n34 = s.short_row_34; a.n2 = s.short_row_2;
+    const int f13 = s.fill0_nnz_short13, f34 = s.fill0_nnz_short34, f22 = s.fill0_nnz_short22;
+    a.s1 = f16 ? f13 + f34 + f22 : 0;
+    a.s13 = f16 ? 0 : s.short_row_1;
+    a.s34 = a.s13 + f13;
+    a.s22 = a.s34 + f34;
+    const int ybase = s.row_long + s.row_block;
+    a.y13 = ybase + (f16 ? 0 : s.short_row_1);
+    a.y34 = a.y13 + 2 * s.common_13;
+    a.y22 = a.y34 + s.short_row_34;
+    a.y1 = f16 ? a.y22 + s.short_row_2 : ybase;
+    a.y0 = s.m - s.row_zero;
+    a.G = f16 ? 32 : 8;
+    a.row_zero = s.row_zero;
+
+    const int tiles13 = cdiv(s.common_13, 8), tiles34 = cdiv(s.short_row_34, 8);
+    const int tiles22 = cdiv(s.short_row_2, 2 * a.G) * (a.G / 8);
+    const int per_cta = WARPS * SHORT_TILES_PER_WARP;
+    a.e_long = cdiv(L.n_long_units, WARPS);
+    a.e_med = a.e_long + cdiv(s.blocknum / 4, WARPS);
+    a.e_s1 = a.e_med + cdiv(s.short_row_1, CTA * SINGLES_PER_THREAD);
+    a.e_s13 = a.e_s1 + cdiv(tiles13, per_cta);
+    a.e_s34 = a.e_s13 + cdiv(tiles34, per_cta);
+    a.e_s22 = a.e_s34 + cdiv(tiles22, per_cta);
+    a.e_zero = a.e_s22 + cdiv(s.row_zero, CTA);
+    if (a.e_zero == 0) return DASP_OK;
+
+    const bool mma_med = !f16 && h->var_medium == DASP_VARIANT_MMA;
+    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
+    if (f16)
+        spmv_kernel<__half, false, false><<<a.e_zero, CTA, 0, st>>>(a);
+    else if (mma_med && mma_long)
+        spmv_kernel<double, true, true><<<a.e_zero, CTA, 0, st>>>(a);
+    else if (mma_med)
+        spmv_kernel<double, true, false><<<a.e_zero, CTA, 0, st>>>(a);
+    else if (mma_long)
+        spmv_kernel<double, false, true><<<a.e_zero, CTA, 0, st>>>(a);
+    else
+        spmv_kernel<double, false, false><<<a.e_zero, CTA, 0, st>>>(a);
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
+} // namespace dasp

@@ -1,0 +1,142 @@
+/*
+ * include/dasp.h — C ABI of the B200-native DASP SpMV (libdasp_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of SuperScientificSoftwareLaboratory/DASP:
+ *   CSR in -> long/medium/short row classification + block re-organisation -> repeatable y = A*x,
+ *   FP64 and FP16.
+ *
+ * The reference exposes that path as ONE monolithic C++ function
+ *     void spmv_all(char *filename, MAT_VAL_TYPE *csrValA, int *csrRowPtrA, int *csrColIdxA,
+ *                   MAT_VAL_TYPE *X_val, MAT_VAL_TYPE *Y_val, int *order_rid,
+ *                   int rowA, int colA, int nnzA, int NUM, double threshold, int block_longest);
+ *     (reference: src/dasp_f64.h:486-487, src/dasp_f16.h:1015-1016; called from
+ *      src/main_f64.cu:149, src/main_f16.cu:146)
+ * which preprocesses on the host, uploads, times 1100 launches and downloads y in PERMUTED order
+ * together with the permutation order_rid.  Here the same surface is split into analyse
+ * (dasp_create) and execute (dasp_spmv) so the product is repeatable; dasp_spmv_all_f64/_f16 keep
+ * the reference's one-shot signature on top of it.
+ *
+ * Conventions: plain pointers and sizes only; every entry returns 0 on success or a negative
+ * dasp_status (the reference checks no CUDA status at all: SURVEY.md §5); a handle is used by one
+ * host thread at a time, distinct handles (one per GPU) are independent; the library owns all
+ * device memory of a handle, the caller owns x, y and the CSR arrays.  There is no CPU fallback:
+ * without a CUDA device every entry fails with DASP_ERR_CUDA.
+ */
+#ifndef DASP_B200_H
+#define DASP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dasp_handle dasp_handle;
+
+/* value type: the reference selects it at compile time with -D f64 (src/common.h:21-25) */
+typedef enum { DASP_F64 = 0, DASP_F16 = 1 } dasp_dtype;
+
+typedef enum {
+    DASP_OK = 0,
+    DASP_ERR_INVALID = -1, /* bad argument (NULL, negative size, unknown name/dtype)      */
+    DASP_ERR_CUDA = -2,    /* a CUDA call failed; dasp_last_error() has the CUDA string   */
+    DASP_ERR_ALLOC = -3,   /* device or host allocation failed                            */
+    DASP_ERR_RANGE = -4,   /* nnz or a padded size does not fit the 32-bit layout         */
+    DASP_ERR_BUFFER = -5   /* dasp_export destination too small                           */
+} dasp_status;
+
+/* SpMV kernel variant per row category (north_star: keep the MMA tile variant only where it
+ * wins on achieved HBM GB/s).  AUTO = the measured winner recorded in profiles/. */
+typedef enum {
+    DASP_VARIANT_AUTO = 0,
+    DASP_VARIANT_CUDA_CORE = 1, /* per-lane 4-wide dot over the 8x4 tiles, 256/128-bit loads */
+    DASP_VARIANT_MMA = 2        /* mma.sync m8n8k4.f64 (DMMA) on the same tiles, as the reference does */
+} dasp_variant;
+
+/* The reference's locals that describe the layout (the 18 structure columns of its CSV record,
+ * src/dasp_f64.h:1440-1441, plus the launch geometry of :1194-1214). All counts, not bytes. */
+typedef struct dasp_stats_t {
+    int dtype, m, n;
+    int64_t nnz;
+    int row_long, row_block, row_zero;
+    int short_row_1, short_row_3, short_row_2, short_row_4; /* after the 1&3 pairing */
+    int common_13, short_row_34;
+    int rowloop, blocknum;
+    int warp_number, BlockNum_long, fill0_nnz_long;
+    int fill0_nnz_reg, nnz_irreg, origin_nnz_reg;
+    int fill0_nnz_short, fill0_nnz_short13, fill0_nnz_short34, fill0_nnz_short22;
+    int threadblock13, threadblock34, threadblock22;
+    int nnz_short, nnz_long;
+    int BlockNum, BlockNum_short_1, BlockNum_all, sumBlockNum;
+    int fill0_nnz_irreg;
+    double rate_fill0;       /* (padded slots - nnz) / nnz, src/dasp_f64.h:1159-1160           */
+    int64_t data_X, data_X2; /* the reference's DASP byte accounting, src/dasp_f64.h:1162-1172 */
+    int64_t data_origin1;    /* CSR ("algorithmic") bytes, src/main_f64.cu:143                 */
+    double preprocess_ms;    /* device time of the GPU preprocessing inside dasp_create        */
+    int64_t device_bytes;    /* device memory held by the handle                               */
+} dasp_stats_t;
+
+/* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,
+ * src/dasp_f16.h:1029-1443) and keep the packed layout resident.  rowptr/colidx/val may be host
+ * or device pointers (detected); val is double[nnz] or IEEE-half[nnz] by dtype; columns need not
+ * be sorted.  threshold/block_longest: the reference's run-time constants 0.75 / 256
+ * (src/main_f64.cu:124-125).  The CSR is not retained. */
+int dasp_create(dasp_handle **h, dasp_dtype dtype, int device, int m, int n, int64_t nnz,
+                const int *rowptr, const int *colidx, const void *val, double threshold,
+                int block_longest);
+
+/* Execute y = A*x, asynchronously on `stream` (a cudaStream_t, NULL = default stream).
+ * d_x: n values, d_y: m values, both device pointers of the handle's dtype.  y is produced in the
+ * reference's PERMUTED order: y[k] belongs to original row order_rid[k] (K11 in SURVEY.md §8a;
+ * kernels replaced: dasp_spmv2 + longPart_sum, src/dasp_f64.h:53-484, src/dasp_f16.h:106-590).
+ * Rows without entries are written as 0 on every call. */
+int dasp_spmv(dasp_handle *h, const void *d_x, void *d_y, void *stream);
+
+/* Same product, y scattered to ORIGINAL row order (y[order_rid[k]]); for solvers that feed y back
+ * as the next x (the power-iteration workload). */
+int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *stream);
+
+/* Host-buffer convenience with the reference's data movement (src/dasp_f64.h:1241,1402): upload x,
+ * run, download y (permuted order), synchronous. */
+int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host);
+
+/* device pointer to order_rid[m] (permuted index -> original row), src/dasp_f64.h:960-976 */
+int dasp_order(const dasp_handle *h, const int **d_order_rid);
+
+int dasp_stats(const dasp_handle *h, dasp_stats_t *out);
+
+/* Copy one preprocessing output to the host for bit-exact checks.  name is one of:
+ * order_rid, long_rpt_new, long_val, long_cid, blockPtr, irreg_rpt, irreg_val, irreg_cid,
+ * reg_val, reg_cid, short_val, short_cid.  *bytes receives the array size; host_dst may be NULL
+ * to query it. */
+int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes,
+                int64_t *bytes);
+
+int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
+
+/* number of kernel launches one dasp_spmv issues (for launch accounting) */
+int dasp_launches_per_spmv(const dasp_handle *h);
+
+int dasp_destroy(dasp_handle *h);
+
+const char *dasp_strerror(int status);
+const char *dasp_last_error(void); /* thread-local detail of the last failure */
+
+/* One-shot calls with the reference's spmv_all argument list (host pointers, y permuted, order_rid
+ * out).  `filename` is only a label, NUM is unused, exactly as in the reference. Returns a status
+ * instead of void. */
+int dasp_spmv_all_f64(const char *filename, const double *csrValA, const int *csrRowPtrA,
+                      const int *csrColIdxA, const double *X_val, double *Y_val, int *order_rid,
+                      int rowA, int colA, int nnzA, int NUM, double threshold, int block_longest);
+int dasp_spmv_all_f16(const char *filename, const void *csrValA, const int *csrRowPtrA,
+                      const int *csrColIdxA, const void *X_val, void *Y_val, int *order_rid,
+                      int rowA, int colA, int nnzA, int NUM, double threshold, int block_longest);
+
+/* nnz-balanced contiguous row partition for multi-GPU runs: cut[p] = smallest i
+ * with rowptr[i] >= p*nnz/parts; cuts has parts+1 entries, cut[0]=0, cut[parts]=m. rowptr: host. */
+int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASP_B200_H */

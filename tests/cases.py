@@ -1,0 +1,68 @@
+"""Named parity cases shared by the CPU (oracle) and GPU (C-ABI) tests.  All are small enough for
+the oracle to finish in well under a second each."""
+from __future__ import annotations
+
+import numpy as np
+
+import matrices as M
+
+
+def _lens(lens, n=None, seed=11, window=None):
+    lens = np.asarray(lens, dtype=np.int64)
+    n = n or max(int(lens.max(initial=1)) + 16, len(lens), 64)
+    return M.from_lengths(lens, n, seed, window=window)
+
+
+def _pairs(k):
+    """k one-rows and k three-rows interleaved with a few others: around the common_13 >= 128 switch"""
+    rng = np.random.default_rng(k)
+    lens = np.array([1] * k + [3] * k + [2] * 37 + [4] * 21 + [0] * 5 + [7] * 40)
+    rng.shuffle(lens)
+    return _lens(lens, seed=k)
+
+
+CASES = {
+    # every category populated (fixture F1 of SURVEY.md Appendix A)
+    "mixed_f1": lambda: M.mixed(),
+    "stencil27_12": lambda: M.stencil27(12),
+    "stencil27_9x7x5": lambda: M.stencil27(9, 7, 5),
+    "powerlaw_20k": lambda: M.powerlaw(),
+    "skewed_long5000": lambda: M.skewed(),
+    "symmetric_like": lambda: M.symmetric_like(),
+    # category edges
+    "only_1": lambda: M.only_lengths(1, 700),
+    "only_2": lambda: M.only_lengths(2, 333),
+    "only_3": lambda: M.only_lengths(3, 129),
+    "only_4": lambda: M.only_lengths(4, 1001),
+    "only_5": lambda: M.only_lengths(5, 77),
+    "len_255_256": lambda: _lens([255] * 9 + [256] * 7 + [257] * 3 + [4, 5] * 10, n=4096),
+    "pairs_127": lambda: _pairs(127),
+    "pairs_128": lambda: _pairs(128),
+    "pairs_129": lambda: _pairs(129),
+    "pairs_1000_vs_300": lambda: _lens([1] * 1000 + [3] * 300 + [2] * 65, seed=3),
+    "empty_rows_only": lambda: _lens([0] * 50, n=64),
+    "zero_rows_mixed": lambda: _lens([0, 9, 0, 0, 300, 1, 0, 2, 0, 3, 4, 0] * 30, n=2048),
+    "one_row_70000": lambda: _lens([70000, 3, 1, 12], n=80000, seed=2),
+    "long_pad_64k": lambda: _lens([64, 65, 128, 129, 4096, 4097] * 3 + [300] * 50, n=8192, seed=4),
+    "ragged_tail_blocks": lambda: _lens(list(range(5, 90)) + [200, 199, 17] * 11, n=1024, seed=6),
+    "rowloop_59989": lambda: _lens([5] * 59989 + [1, 2, 3], n=70000, seed=8, window=64),
+    "rowloop_59990": lambda: _lens([5] * 59990 + [1, 2, 3], n=70000, seed=8, window=64),
+    "rowloop_400000": lambda: _lens([6] * 400000, n=400000, seed=9, window=64),
+}
+
+_cache = {}
+
+
+def get(name):
+    """Generate a case once per process (the big ones take seconds in numpy)."""
+    if name not in _cache:
+        _cache[name] = CASES[name]()
+    return _cache[name]
+
+
+# cheap subset for the no-GPU suite (the big rowloop cases only matter for array lengths)
+CPU_CASES = [k for k in CASES if k not in ("rowloop_400000",)]
+
+
+def x_for(n, seed=7):
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)

@@ -1,0 +1,137 @@
+"""GPU parity tests: the C-ABI library against the oracle, on the same seeded inputs.
+
+* every preprocessing output bit-exact against oracle.preprocess (the restatement pinned to the
+  compiled reference, see tests/test_oracle.py);
+* FP64 y within 1e-12 relative L2 of the serial CSR result, through order_rid (north_star);
+* FP16 y within the reference's own threshold |dy| <= 1 (src/main_f16.cu:10) AND a relative-L2
+  bound so the gate is not vacuous (inputs rounded to half, reference product in double).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from cases import CASES, get, x_for
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-12          # north_star: relative L2 vs the serial CSR result
+FP16_ABS_TOL = 1.0        # the reference's threshold, src/main_f16.cu:10
+FP16_REL_TOL = 2e-3       # fp32 accumulation + one rounding to half (2^-11 ~ 4.9e-4 per element)
+
+SCALARS = ["row_long", "row_block", "row_zero", "short_row_1", "short_row_3", "short_row_2", "short_row_4",
+           "common_13", "short_row_34", "rowloop", "blocknum", "warp_number", "BlockNum_long", "fill0_nnz_long",
+           "fill0_nnz_reg", "nnz_irreg", "origin_nnz_reg", "fill0_nnz_short", "fill0_nnz_short13",
+           "fill0_nnz_short34", "fill0_nnz_short22", "threadblock13", "threadblock34", "threadblock22",
+           "nnz_short", "nnz_long", "BlockNum", "BlockNum_short_1", "BlockNum_all", "sumBlockNum", "fill0_nnz_irreg"]
+
+
+def _rel_l2(a, b):
+    d = np.linalg.norm(a.astype(np.float64) - b.astype(np.float64))
+    nb = np.linalg.norm(b.astype(np.float64))
+    return d / nb if nb > 0 else d
+
+
+@pytest.fixture(scope="module")
+def dasp(cuda_device):
+    import dasp_b200
+
+    dasp_b200.load()
+    return dasp_b200
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
+    import torch
+
+    m, n, rp, ci, v = get(name)
+    npdt = np.float16 if dtype == oracle.F16 else np.float64
+    v = v.astype(npdt)
+    ref = oracle.preprocess(dtype, m, n, rp, ci, v)
+    h = dasp.Dasp(dtype, m, n, rp, ci, v)
+    try:
+        st = h.stats()
+        for s in SCALARS:
+            assert st[s] == ref[s], f"{name}: scalar {s}: {st[s]} != {ref[s]}"
+        for a in dasp.lib.ARRAYS:
+            got = h.export(a)
+            assert got.shape == ref[a].shape, f"{name}: {a} length {got.shape} != {ref[a].shape}"
+            assert np.array_equal(got.view(np.uint8), ref[a].view(np.uint8)), f"{name}: {a} differs"
+
+        x = x_for(n).astype(npdt)
+        if dtype == oracle.F64:
+            y_ref = oracle.csr_spmv_f64(m, rp, ci, v, x)
+        else:
+            y_ref = oracle.csr_spmv_f16(m, rp, ci, v, x)
+        order = ref["order_rid"]
+        tdt = torch.float16 if dtype == oracle.F16 else torch.float64
+        dx = torch.from_numpy(x).to(cuda_device)
+        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA] if dtype == oracle.F64 else [dasp.VARIANT_AUTO]):
+            h.set_variant(variant, variant, variant)
+            for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
+                dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
+                h.spmv(dx, dy, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                y = dy.cpu().numpy()[:m]
+                assert np.all(np.isfinite(y.astype(np.float64))), f"{name}: unwritten y entries (variant {variant})"
+                if dtype == oracle.F64:
+                    assert _rel_l2(y, y_ref[order]) <= FP64_TOL, f"{name} variant {variant}"
+                else:
+                    assert np.max(np.abs(y.astype(np.float64) - y_ref[order]), initial=0.0) <= FP16_ABS_TOL
+                    assert _rel_l2(y, y_ref[order]) <= FP16_REL_TOL, f"{name}"
+            # original-order output
+            dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
+            h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            y = dy.cpu().numpy()[:m]
+            tol = FP64_TOL if dtype == oracle.F64 else FP16_REL_TOL
+            assert _rel_l2(y, y_ref) <= tol, f"{name}: unpermuted"
+    finally:
+        h.close()
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+def test_all_ones_gives_row_lengths(dasp, cuda_device, dtype):
+    """The reference's shipped run sets A and x to 1 (src/main_f64.cu:131-132): y_perm[k] must equal the
+    length of row order_rid[k]; exact in half up to 2048."""
+    m, n, rp, ci, v = get("mixed_f1")
+    npdt = np.float16 if dtype == oracle.F16 else np.float64
+    ones = np.ones(len(v), dtype=npdt)
+    y, order = dasp.spmv_all(dtype, ones, rp, ci, np.ones(n, dtype=npdt), m, n)
+    lens = np.diff(rp)[order]
+    assert np.array_equal(y.astype(np.float64), lens.astype(np.float64))
+    assert sorted(order.tolist()) == list(range(m))
+
+
+def test_spmv_host_matches_device(dasp, cuda_device):
+    m, n, rp, ci, v = get("powerlaw_20k")
+    x = x_for(n)
+    h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)
+    y = h.spmv_host(x)
+    ref = oracle.csr_spmv_f64(m, rp, ci, v, x)
+    assert _rel_l2(y, ref[h.export("order_rid")]) <= FP64_TOL
+    h.close()
+
+
+def test_device_csr_input(dasp, cuda_device):
+    import torch
+
+    m, n, rp, ci, v = get("mixed_f1")
+    d = [torch.from_numpy(a).to(cuda_device) for a in (rp, ci, v)]
+    h = dasp.Dasp(oracle.F64, m, n, d[0], d[1], d[2], nnz=int(rp[m]))
+    ref = oracle.preprocess(oracle.F64, m, n, rp, ci, v)
+    for a in dasp.lib.ARRAYS:
+        assert np.array_equal(h.export(a).view(np.uint8), ref[a].view(np.uint8)), a
+    h.close()
+
+
+def test_bad_arguments_fail_loudly(dasp, cuda_device):
+    m, n, rp, ci, v = get("only_5")
+    with pytest.raises(dasp.DaspError):
+        dasp.Dasp(oracle.F64, m, n, rp, ci, v, threshold=0.0)
+    with pytest.raises(dasp.DaspError):
+        dasp.Dasp(7, m, n, rp, ci, v)
+    h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)
+    with pytest.raises(dasp.DaspError):
+        h.export("no_such_array")
+    h.close()
