@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py — DASP SpMV throughput on B200 (metric of BASELINE.json: GFLOPS = 2*nnz/t and achieved
+HBM GB/s on algorithmic bytes), one JSON line on rank 0.
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload c4|c1|c2|c3|c5] [--impl reference]
+
+A step = one y = A*x over the whole (partitioned) matrix.  Default workload: C4 of BASELINE.json, the
+27-point stencil on 256^3 (16.7 M rows, 449 M nnz, FP64) — the configuration the 1/2/4/8-GPU scaling
+target is quoted on.  With N > 1 (launched by torchrun, one rank per GPU) the matrix is cut into
+nnz-balanced contiguous row slabs, x is replicated, every rank multiplies its slab, no collective on
+the data path (strong scaling); time = max over ranks of the device time of K back-to-back launches.
+
+Keys beyond the base contract: roofline (dominant kernel vs MEASURED_PEAKS.json), cpu_baseline (serial
+CSR loop of oracle/ on host cores, bounded sample), e2e (host buffers through dasp_spmv_host: H2D x,
+kernel, D2H y every step), secondary (cuSPARSE CSR SpMV via torch, and the reference's own DASP kernels
+recompiled for sm_100a from oracle/_ref, on a bounded sample).
+
+--impl reference: the serial-CSR definition of the reference result (oracle/, row-parallel over all host
+threads) on a bounded sample of the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--grid", type=int, default=256, help="c4: stencil grid edge")
+    ap.add_argument("--scale", type=float, default=1.0, help="c3/c5: fraction of the named size")
+    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+
+def make_spec(args):
+    from dasp_b200 import synth
+
+    w = args.workload
+    if w == "c4":
+        g = args.grid
+        return synth.stencil27(g), f"C4 27-point stencil {g}^3 fp64", False
+    if w in ("c1", "c2"):
+        half = w == "c2"
+        return synth.banded(), ("C2" if half else "C1") + " cop20k_A stand-in (banded symmetric, seed 7; real .mtx is a missing blob) " + ("fp16" if half else "fp64"), half
+    if w == "c3":
+        m = int(10_000_000 * args.scale)
+        return synth.powerlaw(m=m), f"C3 power-law alpha=0.95 {m} rows fp64", False
+    m = int(50_000_000 * args.scale)
+    nl = max(1, int(1000 * args.scale))
+    return synth.skewed(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows in a common 2^21 band + {m} short rows fp64", False
+
+
+def algorithmic_bytes(m, n, nnz, esz):
+    """CSR bytes, x read once, y written once: the reference's data_origin1 (src/main_f64.cu:143)."""
+    return nnz * (esz + 4) + (m + 1) * 4 + n * esz + m * esz
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"
+    return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: serial-CSR definition on host cores, bounded sample
+
+def host_sample(args, spec, target_nnz=60_000_000):
+    """First rows of the workload holding about target_nnz entries, as host CSR (float64)."""
+    import torch
+
+    from dasp_b200 import synth
+
+    if torch.cuda.is_available():
+        dev = torch.device("cuda:0")
+        ln = synth.row_lengths(spec, 0, spec.m, dev)
+        cs = torch.cumsum(ln, 0)
+        rows = int(torch.searchsorted(cs, torch.tensor([target_nnz], device=dev)).item()) + 1
+        rows = min(rows, spec.m)
+        del ln, cs
+        rp, ci, v, nnz = synth.generate(spec, 0, rows, dev)
+        out = (rows, spec.n, rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy())
+        del rp, ci, v
+        torch.cuda.empty_cache()
+        return out
+    # no GPU: numpy twin (stencil only)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import matrices
+
+    m, n, rp, ci, v = matrices.stencil27(min(args.grid, 96))
+    return m, n, rp, ci, v
+
+
+def cpu_leg(args, spec, threads, steps, warmup):
+    import oracle
+
+    m, n, rp, ci, v = host_sample(args, spec)
+    nnz = int(rp[m])
+    x = np.random.default_rng(7).uniform(-1, 1, n)
+    for _ in range(max(1, min(warmup, 2))):
+        oracle.csr_spmv_f64(m, rp, ci, v, x, threads=threads)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.csr_spmv_f64(m, rp, ci, v, x, threads=threads)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    return {"value": 2.0 * nnz / t / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+            "sample": f"rows [0,{m}) of the workload ({nnz} nnz), serial CSR loop per thread, mean of {steps} passes",
+            "ms_per_step": t * 1e3,
+            "hbm_gbs": algorithmic_bytes(m, n, nnz, 8) / t / 1e9}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, wname, half = make_spec(args)
+    threads = os.cpu_count() or 1
+    steps = max(3, min(args.steps, 10))
+    leg = cpu_leg(args, spec, threads, steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "spmv_gflops", "value": leg["value"], "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": leg["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, "note": "the reference ships no CPU SpMV; this is the serial CSR loop that defines its result (oracle/), row-parallel on all host threads"},
+        "hbm_gbs": leg["hbm_gbs"],
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": leg["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import dasp_b200
+    from dasp_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dasp_b200.load()
+
+    spec, wname, half = make_spec(args)
+    esz = 2 if half else 8
+    tdt = torch.float16 if half else torch.float64
+    dtype = dasp_b200.DASP_F16 if half else dasp_b200.DASP_F64
+    m, n = int(spec.m), int(spec.n)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # nnz-balanced contiguous row slabs: cut p = smallest i with rowptr[i] >= p*nnz/P
+    ln = synth.row_lengths(spec, 0, m, dev)
+    cs = torch.cumsum(ln, 0)  # cs[i] = rowptr[i+1]
+    nnz_total = int(cs[-1].item())
+    targets = torch.tensor([nnz_total * p // world for p in range(1, world)], device=dev, dtype=torch.int64)
+    cuts = [0] + [int(c) + 1 for c in torch.searchsorted(cs, targets, right=False).tolist()] + [m]
+    cuts = [min(c, m) for c in cuts]
+    del ln, cs
+    r0, r1 = cuts[rank], cuts[rank + 1]
+
+    rp, ci, v, nnz = synth.generate(spec, r0, r1, dev, half=half)
+    t0 = time.perf_counter()
+    h = dasp_b200.Dasp(dtype, r1 - r0, n, rp, ci, v, device=local, nnz=nnz)
+    create_s = time.perf_counter() - t0
+    st = h.stats()
+    var = {"auto": 0, "cuda": 1, "mma": 2}[args.variant]
+    h.set_variant(var, var, var)
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    x = (torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdt)
+    y = torch.zeros(max(r1 - r0, 1), dtype=tdt, device=dev)
+
+    # bounded parity check inside the bench: first rows of this slab against the serial CSR oracle
+    chk_rows = min(r1 - r0, 20000)
+    chk = None
+    if chk_rows > 0 and not half:
+        import oracle
+
+        rp_h = rp[: chk_rows + 1].cpu().numpy()
+        k = int(rp_h[-1])
+        y_ref = oracle.csr_spmv_f64(chk_rows, rp_h, ci[:k].cpu().numpy(), v[:k].cpu().numpy(), x.cpu().numpy())
+        yy = torch.empty_like(y)
+        h.spmv_unpermuted(x, yy, stream)
+        torch.cuda.synchronize(dev)
+        got = yy[:chk_rows].cpu().numpy()
+        chk = float(np.linalg.norm(got - y_ref) / max(np.linalg.norm(y_ref), 1e-300))
+        if chk > 1e-12:
+            raise SystemExit(f"bench.py: parity check failed, relative L2 {chk}")
+
+    keep_csr = (world == 1 and not args.no_secondary and not half)
+    if not keep_csr:
+        del rp, ci, v
+        torch.cuda.empty_cache()
+
+    small = algorithmic_bytes(r1 - r0, n, nnz, esz) < 256e6
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev) if (small and args.cold) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(steps, warmup):
+        for _ in range(warmup):
+            h.spmv(x, y, stream)
+        barrier()
+        if flush is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                h.spmv(x, y, stream)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+        else:
+            ms = 0.0
+            for _ in range(steps):
+                synth.flush_l2(flush)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                h.spmv(x, y, stream)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms += e0.elapsed_time(e1)
+        barrier()
+        return ms
+
+    with ClockSampler(local) as clk:
+        ms_local = timed(args.steps, args.warmup)
+    t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # end to end through the C ABI with host buffers: H2D x, kernel, D2H y every step
+    hx = torch.empty(n, dtype=tdt).pin_memory()
+    hx.copy_(x.cpu())
+    hy = torch.empty(max(r1 - r0, 1), dtype=tdt).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        h.spmv_host(hx, hy)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h.spmv_host(hx, hy)
+    torch.cuda.synchronize(dev)
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    b_alg_total = algorithmic_bytes(m, n, nnz_total, esz)
+    b_alg_rank = algorithmic_bytes(r1 - r0, n, nnz, esz)
+    ach = b_alg_rank / (ms_local / args.steps * 1e-3) / 1e9
+    line = {
+        "metric": "spmv_gflops", "value": 2.0 * nnz_total / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16" if half else "f64", "data": "synthetic",
+        "config": {"workload": wname, "m": m, "n": n, "nnz": nnz_total, "seed": int(spec.seed),
+                   "partition": "nnz-balanced contiguous row slabs, x replicated" if world > 1 else "single GPU",
+                   "l2": ("L2 flushed before every launch" if flush is not None else
+                          ("inputs exceed L2 (%.0f MB per rank)" % (b_alg_rank / 1e6) if not small else
+                           "warm L2: back-to-back launches on an L2-resident matrix (reference protocol, src/dasp_f64.h:1301-1311)")),
+                   "variant": args.variant, "threshold": 0.75, "block_longest": 256},
+        "hbm_gbs": b_alg_total / (ms_step * 1e-3) / 1e9,
+        "hbm_frac_of_8tbs": b_alg_total / (ms_step * 1e-3) / 8e12 / world,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "kernel": "spmv_kernel (fused, rank 0 slab)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": b_alg_rank},
+        "gpu_launches": args.steps * h.launches_per_spmv(),
+        "clocks": clk.summary(),
+        "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+                "h2d_bytes_per_step": n * esz, "d2h_bytes_per_step": (r1 - r0) * esz, "ms_per_step": e2e_ms,
+                "path": "dasp_spmv_host (pinned host x -> device, fused kernel, device y -> pinned host), per rank"},
+        "preprocess": {"gpu_ms": st["preprocess_ms"], "create_wall_s": create_s, "rate_fill0": st["rate_fill0"],
+                       "row_long": st["row_long"], "row_block": st["row_block"], "short_rows": st["short_row_1"] + 2 * st["common_13"] + st["short_row_34"] + st["short_row_2"],
+                       "device_bytes": st["device_bytes"]},
+        "parity_check_rel_l2": chk,
+    }
+
+    if world == 1 and not args.no_cpu and not half:
+        try:
+            leg = cpu_leg(args, spec, 1, 3, 1)
+            line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
+        except Exception as e:  # the CPU leg must never take the GPU number down with it
+            line["cpu_baseline"] = {"error": repr(e)}
+
+    if keep_csr:
+        sec = {}
+        try:  # cuSPARSE CSR SpMV through torch (bench only, never on the product path)
+            A = torch.sparse_csr_tensor(rp, ci, v, size=(m, n))
+            for _ in range(3):
+                yc = A @ x
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks = max(3, min(args.steps, 10))
+            e0.record()
+            for _ in range(ks):
+                yc = A @ x
+            e1.record()
+            torch.cuda.synchronize(dev)
+            cms = e0.elapsed_time(e1) / ks
+            sec["cusparse_csr"] = {"gflops": 2.0 * nnz_total / (cms * 1e-3) / 1e9, "ms": cms,
+                                   "hbm_gbs": b_alg_total / (cms * 1e-3) / 1e9, "via": "torch.sparse_csr @ x"}
+            del A, yc
+        except Exception as e:
+            sec["cusparse_csr"] = {"error": repr(e)}
+        del rp, ci, v
+        torch.cuda.empty_cache()
+        try:
+            sec["ref_dasp_sm100a"] = reference_kernels_leg(args, dev)
+        except Exception as e:
+            sec["ref_dasp_sm100a"] = {"error": repr(e)}
+        line["secondary"] = sec
+
+    print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_kernels_leg(args, dev):
+    """The reference's own kernels (unmodified, recompiled for sm_100a: oracle/_ref) and ours on the same
+    bounded sample: a 128^3 stencil (the reference preprocesses on one host thread)."""
+    import torch
+
+    import dasp_b200
+    import oracle
+    from dasp_b200 import synth
+
+    if not oracle.ref_available(oracle.F64):
+        return {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+    g = min(args.grid, 128)
+    spec = synth.stencil27(g)
+    rp, ci, v, nnz = synth.generate(spec, 0, spec.m, dev)
+    rp_h, ci_h, v_h = rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy()
+    m = int(spec.m)
+    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, m, rp, ci, v, nnz=nnz)
+    x = torch.ones(m, dtype=torch.float64, device=dev)
+    y = torch.empty(m, dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    for _ in range(20):
+        h.spmv(x, y, s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        h.spmv(x, y, s)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ours_ms = e0.elapsed_time(e1) / 200
+    h.close()
+    del rp, ci, v
+    r = oracle.ref_spmv_all(oracle.F64, m, m, rp_h, ci_h, v_h, x=np.ones(m))
+    cols = r["csv"].split(",")
+    ref_ms = float(cols[21])  # dasp_time of the CSV record, src/dasp_f64.h:1441
+    y_ref = oracle.csr_spmv_f64(m, rp_h, ci_h, v_h, np.ones(m))
+    ref_err = float(np.linalg.norm(r["y_perm"] - y_ref[r["order_rid"]]) / np.linalg.norm(y_ref)) if r["ran_on_gpu"] else None
+    return {"sample": f"27-point stencil {g}^3 ({nnz} nnz), reference protocol: 100 warm + 1000 timed launches, gettimeofday",
+            "ref_ms": ref_ms, "ref_gflops": 2.0 * nnz / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else None,
+            "ours_ms": ours_ms, "ours_gflops": 2.0 * nnz / (ours_ms * 1e-3) / 1e9,
+            "ran_on_gpu": r["ran_on_gpu"], "ref_y_rel_l2_vs_serial_csr": ref_err}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,256 @@
+// synth.cu — device-side generators for the benchmark matrices (include/dasp_synth.h).
+// Bench/test tooling only; not linked into libdasp_b200.so.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/dasp_synth.h"
+
+namespace {
+
+thread_local char g_err[256] = "";
+int fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return -2;
+}
+#define SYNTH_LAUNCH_CHECK(what)                          \
+    do {                                                  \
+        cudaError_t e_ = cudaGetLastError();              \
+        if (e_ != cudaSuccess) return fail(e_, what);     \
+    } while (0)
+
+// splitmix64 finaliser as a counter-based generator
+__host__ __device__ inline uint64_t mix(uint64_t z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t h3(uint64_t seed, uint64_t a, uint64_t b) { return mix(mix(seed ^ mix(a)) + b); }
+__host__ __device__ inline double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); } // [0,1)
+__host__ __device__ inline double sym(uint64_t h) { return 2.0 * u01(h) - 1.0; }                              // [-1,1)
+
+__device__ inline int64_t next_pow2(int64_t v)
+{
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------- stencil27
+__device__ inline int cnt1(int c, int n) { return 1 + (c > 0) + (c < n - 1); }
+
+__global__ void stencil_len(dasp_synth_spec s, int64_t row0, int64_t rows, int *len)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    int64_t i = row0 + t;
+    int x = (int)(i % s.nx), y = (int)((i / s.nx) % s.ny), z = (int)(i / ((int64_t)s.nx * s.ny));
+    len[t] = cnt1(x, s.nx) * cnt1(y, s.ny) * cnt1(z, s.nz);
+}
+
+__global__ void stencil_fill(dasp_synth_spec s, int64_t row0, int64_t rows, const int *rowptr, int *colidx, double *val)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    int64_t i = row0 + t;
+    int x = (int)(i % s.nx), y = (int)((i / s.nx) % s.ny), z = (int)(i / ((int64_t)s.nx * s.ny));
+    int64_t p = rowptr[t];
+    int k = 0;
+    for (int dz = -1; dz <= 1; dz++) {
+        int z2 = z + dz;
+        if (z2 < 0 || z2 >= s.nz) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            int y2 = y + dy;
+            if (y2 < 0 || y2 >= s.ny) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                int x2 = x + dx;
+                if (x2 < 0 || x2 >= s.nx) continue;
+                colidx[p] = (int)(x2 + (int64_t)s.nx * (y2 + (int64_t)s.ny * z2));
+                val[p] = sym(h3(s.seed, (uint64_t)i, (uint64_t)k));
+                p++; k++;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- powerlaw / skewed (element-parallel fill)
+__device__ inline int powerlaw_len(const dasp_synth_spec &s, int64_t i)
+{
+    double u = 1.0 - u01(h3(s.seed, (uint64_t)i, 0x51ull)); // (0,1]
+    double l = floor(pow(u, -1.0 / s.alpha));
+    if (!(l < (double)s.lmax)) l = (double)s.lmax;
+    return l < 0 ? 0 : (int)l;
+}
+
+__device__ inline int skewed_len(const dasp_synth_spec &s, int64_t i)
+{
+    if (i < s.n_long) return s.long_len;
+    return 1 + (int)(h3(s.seed, (uint64_t)i, 0x52ull) & 3);
+}
+
+__global__ void plsk_len(dasp_synth_spec s, int64_t row0, int64_t rows, int *len)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    len[t] = s.kind == 1 ? powerlaw_len(s, row0 + t) : skewed_len(s, row0 + t);
+}
+
+// distinct pseudo-random points of a power-of-two window: k -> lo + ((a*k + b) mod W), a odd
+__device__ inline int64_t window_col(const dasp_synth_spec &s, int64_t i, int64_t k, int len, int64_t halfw)
+{
+    int64_t W = next_pow2(2 * (halfw > len ? halfw : (int64_t)len));
+    while (W > s.n && W > 1) W >>= 1;
+    int64_t c = (int64_t)((double)i * (double)s.n / (double)s.m);
+    int64_t lo = c - W / 2;
+    if (lo < 0) lo = 0;
+    if (lo > s.n - W) lo = s.n - W;
+    uint64_t hr = h3(s.seed, (uint64_t)i, 0x53ull);
+    uint64_t a = (hr | 1ull), b = hr >> 17;
+    return lo + (int64_t)((a * (uint64_t)k + b) & (uint64_t)(W - 1));
+}
+
+__global__ void plsk_fill(dasp_synth_spec s, int64_t row0, int64_t rows, const int *rowptr, int64_t nnz, int *colidx,
+                          double *val)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    // row of element e: last t with rowptr[t] <= e
+    int64_t lo = 0, hi = rows;
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] <= e) lo = mid; else hi = mid;
+    }
+    const int64_t t = lo, i = row0 + t, k = e - rowptr[t];
+    const int len = rowptr[t + 1] - rowptr[t];
+    int64_t col;
+    if (s.kind == 2 && i < s.n_long) {
+        uint64_t hr = h3(s.seed, (uint64_t)i, 0x54ull);
+        uint64_t a = (hr | 1ull), b = hr >> 17;
+        col = s.band_lo + (int64_t)((a * (uint64_t)k + b) & (uint64_t)(s.band - 1));
+    } else {
+        uint64_t hk = h3(s.seed ^ 0xabcdefull, (uint64_t)i, (uint64_t)k);
+        if (s.kind == 1 && hk % 10 == 0) col = (int64_t)((hk >> 8) % (uint64_t)s.n); // 10 % global
+        else col = window_col(s, i, k, len, s.window);
+    }
+    colidx[e] = (int)col;
+    val[e] = sym(h3(s.seed, (uint64_t)i, (uint64_t)k));
+}
+
+// ---------------------------------------------------------------- banded symmetric (cop20k_A stand-in)
+// entry (i,j), j != i, exists iff hash(min,max) < p; p = (mean_len-1)/(2*window); diagonal always present.
+__device__ inline bool band_edge(const dasp_synth_spec &s, int64_t i, int64_t j)
+{
+    if (j < 0 || j >= s.n) return false;
+    if (i == j) return true;
+    int64_t a = i < j ? i : j, b = i < j ? j : i;
+    double p = (double)(s.mean_len - 1) / (2.0 * s.window);
+    return u01(h3(s.seed, (uint64_t)a, (uint64_t)b)) < p;
+}
+
+template <bool FILL>
+__global__ void band_kernel(dasp_synth_spec s, int64_t row0, int64_t rows, int *len, const int *rowptr, int *colidx,
+                            double *val)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; // one warp per row
+    if (t >= rows) return;
+    const int64_t i = row0 + t;
+    int count = 0;
+    int64_t p = FILL ? rowptr[t] : 0;
+    for (int64_t j0 = i - s.window; j0 <= i + s.window; j0 += 32) {
+        int64_t j = j0 + lane;
+        bool ok = j <= i + s.window && band_edge(s, i, j);
+        unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) {
+            int64_t q = p + count + __popc(b & ((1u << lane) - 1u));
+            colidx[q] = (int)j;
+            int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+            val[q] = sym(h3(s.seed ^ 0x77ull, (uint64_t)lo, (uint64_t)hi));
+        }
+        count += __popc(b);
+    }
+    if (!FILL && lane == 0) len[t] = count;
+}
+
+__global__ void to_half_kernel(const double *src, __half *dst, int64_t n)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = __double2half(src[t]);
+}
+
+__global__ void flush_kernel(uint4 *p, int64_t n)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) p[t] = make_uint4((unsigned)t, 1u, 2u, 3u);
+}
+
+inline unsigned blocks(int64_t n, int th) { return (unsigned)((n + th - 1) / th); }
+
+} // namespace
+
+extern "C" {
+
+const char *dasp_synth_last_error(void) { return g_err; }
+
+int dasp_synth_rowlen(const dasp_synth_spec *spec, int64_t row0, int64_t row1, int *d_len, void *stream)
+{
+    if (!spec || row1 < row0 || !d_len) { snprintf(g_err, sizeof(g_err), "bad argument"); return -1; }
+    const int64_t rows = row1 - row0;
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (spec->kind) {
+    case 0: stencil_len<<<blocks(rows, 256), 256, 0, st>>>(*spec, row0, rows, d_len); break;
+    case 1:
+    case 2: plsk_len<<<blocks(rows, 256), 256, 0, st>>>(*spec, row0, rows, d_len); break;
+    case 3: band_kernel<false><<<blocks(rows * 32, 256), 256, 0, st>>>(*spec, row0, rows, d_len, nullptr, nullptr, nullptr); break;
+    default: snprintf(g_err, sizeof(g_err), "unknown kind %d", spec->kind); return -1;
+    }
+    SYNTH_LAUNCH_CHECK("rowlen");
+    return 0;
+}
+
+int dasp_synth_fill(const dasp_synth_spec *spec, int64_t row0, int64_t row1, const int *d_rowptr, int *d_colidx,
+                    double *d_val, void *stream)
+{
+    if (!spec || row1 < row0 || !d_rowptr) { snprintf(g_err, sizeof(g_err), "bad argument"); return -1; }
+    const int64_t rows = row1 - row0;
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (spec->kind) {
+    case 0: stencil_fill<<<blocks(rows, 128), 128, 0, st>>>(*spec, row0, rows, d_rowptr, d_colidx, d_val); break;
+    case 1:
+    case 2: {
+        int nnz = 0;
+        cudaError_t e = cudaMemcpyAsync(&nnz, d_rowptr + rows, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(e, "read nnz");
+        if (nnz > 0) plsk_fill<<<blocks(nnz, 256), 256, 0, st>>>(*spec, row0, rows, d_rowptr, nnz, d_colidx, d_val);
+        break;
+    }
+    case 3: band_kernel<true><<<blocks(rows * 32, 256), 256, 0, st>>>(*spec, row0, rows, nullptr, d_rowptr, d_colidx, d_val); break;
+    default: snprintf(g_err, sizeof(g_err), "unknown kind %d", spec->kind); return -1;
+    }
+    SYNTH_LAUNCH_CHECK("fill");
+    return 0;
+}
+
+int dasp_synth_to_half(const double *d_src, void *d_dst, int64_t count, void *stream)
+{
+    if (count > 0) to_half_kernel<<<blocks(count, 256), 256, 0, (cudaStream_t)stream>>>(d_src, (__half *)d_dst, count);
+    SYNTH_LAUNCH_CHECK("to_half");
+    return 0;
+}
+
+int dasp_synth_flush_l2(void *d_scratch, int64_t bytes, void *stream)
+{
+    int64_t n = bytes / 16;
+    if (n > 0) flush_kernel<<<blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_scratch, n);
+    SYNTH_LAUNCH_CHECK("flush_l2");
+    return 0;
+}
+
+} // extern "C"

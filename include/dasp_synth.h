@@ -1,0 +1,54 @@
+/*
+ * include/dasp_synth.h — synthetic CSR generators for the benchmark configurations of
+ * BASELINE.json (libdasp_synth.so).  Bench/test tooling, not part of the SpMV product: the
+ * reference reads Matrix Market files (src/mmio_highlevel.h:608) and ships no generator; a
+ * 450 M-nnz text file is not a viable input, so the named shapes are generated directly in device
+ * memory.  Every generator is a pure function of (parameters, seed, row): any rank can produce any
+ * row slab [row0, row1) of the same global matrix, with GLOBAL column indices.
+ *
+ * Usage: call *_rowlen to fill len[row1-row0] (device), exclusive-scan it into rowptr (caller),
+ * then call *_fill with that rowptr to write colidx/val (device).  Values are U(-1,1) from a
+ * counter-based hash of (seed, row, k).  All pointers are device pointers; `stream` is a
+ * cudaStream_t.  Returns 0 or a negative code (CUDA error string via dasp_synth_last_error).
+ */
+#ifndef DASP_SYNTH_H
+#define DASP_SYNTH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dasp_synth_spec {
+    int kind;        /* 0 stencil27, 1 powerlaw, 2 skewed, 3 banded-symmetric (cop20k_A stand-in) */
+    int64_t m, n;    /* global rows / columns */
+    uint64_t seed;
+    /* stencil27: grid nx*ny*nz, natural ordering (x fastest), columns ascending */
+    int nx, ny, nz;
+    /* powerlaw: L = min(floor(u^(-1/alpha)), lmax), u ~ U(0,1]; 90 % of the columns of a row are
+       distinct points of a window around i*n/m (half-width max(window, L)), 10 % uniform global */
+    double alpha;
+    int lmax, window;
+    /* skewed: rows [0, n_long) have long_len entries, distinct, unsorted, inside one common band of
+       width band (power of two >= 2*long_len) starting at band_lo; the other rows have L uniform in
+       {1,2,3,4} with columns in a +-window window */
+    int n_long, long_len;
+    int64_t band_lo, band;
+    /* banded-symmetric: structurally symmetric pattern, row lengths ~ mean_len */
+    int mean_len;
+} dasp_synth_spec;
+
+int dasp_synth_rowlen(const dasp_synth_spec *spec, int64_t row0, int64_t row1, int *d_len, void *stream);
+int dasp_synth_fill(const dasp_synth_spec *spec, int64_t row0, int64_t row1, const int *d_rowptr, int *d_colidx,
+                    double *d_val, void *stream);
+/* double -> IEEE half (round to nearest even), for the FP16 configurations */
+int dasp_synth_to_half(const double *d_src, void *d_dst, int64_t count, void *stream);
+/* writes more than the L2 capacity so the next kernel starts cold */
+int dasp_synth_flush_l2(void *d_scratch, int64_t bytes, void *stream);
+const char *dasp_synth_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
