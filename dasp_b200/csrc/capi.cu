@@ -159,6 +159,26 @@ int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *strea
     return launch_spmv(h, d_x, d_y, h->L.order_rid, (cudaStream_t)stream);
 }
 
+int dasp_spmv_timed(dasp_handle *h, const void *d_x, void *d_y, void *stream, int warmup, int reps, float *total_ms)
+{
+    if (!h || !total_ms || reps < 1 || warmup < 0) { set_error("dasp_spmv_timed: bad argument"); return DASP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < warmup; i++) DASP_TRY(launch_spmv(h, d_x, d_y, nullptr, st));
+    cudaEvent_t e0, e1;
+    DASP_CUDA(cudaEventCreate(&e0));
+    DASP_CUDA(cudaEventCreate(&e1));
+    DASP_CUDA(cudaEventRecord(e0, st));
+    int rc = DASP_OK;
+    for (int i = 0; i < reps && rc == DASP_OK; i++) rc = launch_spmv(h, d_x, d_y, nullptr, st);
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (rc == DASP_OK && e != cudaSuccess) { set_error("dasp_spmv_timed: %s", cudaGetErrorString(e)); rc = DASP_ERR_CUDA; }
+    if (rc == DASP_OK) cudaEventElapsedTime(total_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host)
 {
     if (!h || (!x_host && h->L.s.n > 0) || (!y_host && h->L.s.m > 0)) { set_error("dasp_spmv_host: NULL argument"); return DASP_ERR_INVALID; }

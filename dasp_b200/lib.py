@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         L.dasp_spmv.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_unpermuted.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_host.argtypes = [vp, vp, vp]
+        L.dasp_spmv_timed.argtypes = [vp, vp, vp, vp, ip, ip, C.POINTER(C.c_float)]
         L.dasp_order.argtypes = [vp, C.POINTER(vp)]
         L.dasp_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.dasp_export.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
@@ -145,6 +146,13 @@ class Dasp:
 
     def spmv_unpermuted(self, d_x, d_y, stream: int = 0) -> None:
         _check(load().dasp_spmv_unpermuted(self._h, _ptr(d_x), _ptr(d_y), C.c_void_p(stream)), "dasp_spmv_unpermuted")
+
+    def spmv_timed(self, d_x, d_y, stream: int = 0, warmup: int = 0, reps: int = 1) -> float:
+        """`reps` back-to-back launches issued from C; returns their total device time in ms."""
+        ms = C.c_float(0.0)
+        _check(load().dasp_spmv_timed(self._h, _ptr(d_x), _ptr(d_y), C.c_void_p(stream), warmup, reps, C.byref(ms)),
+               "dasp_spmv_timed")
+        return float(ms.value)
 
     def spmv_host(self, x_host, y_host=None):
         """Host buffers in, host buffers out (H2D x, kernel, D2H y); y in permuted order."""

@@ -100,6 +100,12 @@ int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *strea
  * run, download y (permuted order), synchronous. */
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host);
 
+/* The reference's measurement loop (src/dasp_f64.h:1285-1320: warm-up launches, then `reps` launches
+ * back to back) issued from C so that small matrices are not bound by the caller's launch rate, timed
+ * with CUDA events on `stream`.  *total_ms receives the device time of the `reps` launches. */
+int dasp_spmv_timed(dasp_handle *h, const void *d_x, void *d_y, void *stream, int warmup, int reps,
+                    float *total_ms);
+
 /* device pointer to order_rid[m] (permuted index -> original row), src/dasp_f64.h:960-976 */
 int dasp_order(const dasp_handle *h, const int **d_order_rid);
 
