@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--grid", type=int, default=256, help="c4: stencil grid edge")
     ap.add_argument("--scale", type=float, default=1.0, help="c3/c5: fraction of the named size")
-    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split"])
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
@@ -67,7 +67,7 @@ def make_spec(args):
         return synth.powerlaw(m=m), f"C3 power-law alpha=0.95 {m} rows fp64", False
     m = int(50_000_000 * args.scale)
     nl = max(1, int(1000 * args.scale))
-    return synth.skewed(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows in a common 2^21 band + {m} short rows fp64", False
+    return synth.skewed(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows (ascending columns, 50% of a common 2^21 band) + {m} short rows fp64", False
 
 
 def algorithmic_bytes(m, n, nnz, esz):
@@ -247,7 +247,7 @@ def run_ours(args):
     h = dasp_b200.Dasp(dtype, r1 - r0, n, rp, ci, v, device=local, nnz=nnz)
     create_s = time.perf_counter() - t0
     st = h.stats()
-    var = {"auto": 0, "cuda": 1, "mma": 2}[args.variant]
+    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3}[args.variant]
     h.set_variant(var, var, var)
 
     gen = torch.Generator(device=dev)

@@ -72,61 +72,73 @@ __device__ __forceinline__ void from_acc(__half *p, float v) { *p = __float2half
 // ---- streaming loads of the packed matrix: read once, so keep them out of L1 and mark them evict-first in
 // L2 (x must survive there).  Only the 256-bit form takes .L2::evict_first directly; narrower loads go
 // through a createpolicy descriptor.
-__device__ __forceinline__ uint64_t make_stream_policy()
+// keep != 0: the whole layout fits in L2 (small matrices iterated back to back), so it is left at normal
+// priority and later launches hit in L2; otherwise evict-first.
+// (compile-time: only the 256-bit load form takes the L2 priority as an instruction modifier)
+struct StreamPol {
+    uint64_t desc;
+};
+template <bool KEEP> __device__ __forceinline__ StreamPol make_stream_policy()
 {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
+    StreamPol p;
+    if (KEEP) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.desc));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.desc));
+    return p;
 }
 #define DASP_LD_HINT "ld.global.nc.L1::no_allocate.L2::cache_hint"
-__device__ __forceinline__ void ld_stream4(const double *p, double (&v)[4], uint64_t)
+template <bool KEEP> __device__ __forceinline__ void ld_stream4d(const double *p, double (&v)[4])
 {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    if (KEEP)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
-__device__ __forceinline__ void ld_stream4(const __half *p, __half (&v)[4], uint64_t pol)
+template <bool KEEP> __device__ __forceinline__ void ld_stream4(const double *p, double (&v)[4], const StreamPol &) { ld_stream4d<KEEP>(p, v); }
+template <bool KEEP> __device__ __forceinline__ void ld_stream4(const __half *p, __half (&v)[4], const StreamPol &pol)
 {
     unsigned a, b;
-    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol.desc));
     __half2 h0 = *reinterpret_cast<__half2 *>(&a), h1 = *reinterpret_cast<__half2 *>(&b);
     v[0] = __low2half(h0); v[1] = __high2half(h0); v[2] = __low2half(h1); v[3] = __high2half(h1);
 }
-__device__ __forceinline__ void ld_stream4(const int *p, int (&v)[4], uint64_t pol)
+template <bool KEEP> __device__ __forceinline__ void ld_stream4(const int *p, int (&v)[4], const StreamPol &pol)
 {
     asm volatile(DASP_LD_HINT ".v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p), "l"(pol));
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p), "l"(pol.desc));
 }
-__device__ __forceinline__ void ld_stream2(const double *p, double (&v)[2], uint64_t pol)
+__device__ __forceinline__ void ld_stream2(const double *p, double (&v)[2], const StreamPol &pol)
 {
-    asm volatile(DASP_LD_HINT ".v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol.desc));
 }
-__device__ __forceinline__ void ld_stream2(const __half *p, __half (&v)[2], uint64_t pol)
+__device__ __forceinline__ void ld_stream2(const __half *p, __half (&v)[2], const StreamPol &pol)
 {
     unsigned a;
-    asm volatile(DASP_LD_HINT ".u32 %0, [%1], %2;" : "=r"(a) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".u32 %0, [%1], %2;" : "=r"(a) : "l"(p), "l"(pol.desc));
     __half2 h = *reinterpret_cast<__half2 *>(&a);
     v[0] = __low2half(h); v[1] = __high2half(h);
 }
-__device__ __forceinline__ void ld_stream2(const int *p, int (&v)[2], uint64_t pol)
+__device__ __forceinline__ void ld_stream2(const int *p, int (&v)[2], const StreamPol &pol)
 {
-    asm volatile(DASP_LD_HINT ".v2.s32 {%0,%1}, [%2], %3;" : "=r"(v[0]), "=r"(v[1]) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".v2.s32 {%0,%1}, [%2], %3;" : "=r"(v[0]), "=r"(v[1]) : "l"(p), "l"(pol.desc));
 }
-__device__ __forceinline__ double ld_stream1(const double *p, uint64_t pol)
+__device__ __forceinline__ double ld_stream1(const double *p, const StreamPol &pol)
 {
     double v;
-    asm volatile(DASP_LD_HINT ".f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol.desc));
     return v;
 }
-__device__ __forceinline__ __half ld_stream1(const __half *p, uint64_t pol)
+__device__ __forceinline__ __half ld_stream1(const __half *p, const StreamPol &pol)
 {
     unsigned short v;
-    asm volatile(DASP_LD_HINT ".u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol.desc));
     return __ushort_as_half(v);
 }
-__device__ __forceinline__ int ld_stream1(const int *p, uint64_t pol)
+__device__ __forceinline__ int ld_stream1(const int *p, const StreamPol &pol)
 {
     int v;
-    asm volatile(DASP_LD_HINT ".s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    asm volatile(DASP_LD_HINT ".s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol.desc));
     return v;
 }
 
@@ -157,10 +169,10 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 // ------------------------------------------------------------------------------------------------
 // long rows
 
-template <typename T, bool MMA>
+template <typename T, bool MMA, bool KEEP>
 __device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
 {
-    const uint64_t pol = make_stream_policy();
+    const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     const int u = cta * WARPS + (threadIdx.x >> 5);
@@ -196,27 +208,24 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
         double d = (n0 == grp ? c[0] : 0.0) + (n0 + 1 == grp ? c[1] : 0.0);
         acc = (A)warp_sum(d);
     } else {
+        // 32 slots per warp load (lane, lane+32, ...): fully coalesced value/index streams and, for ascending
+        // columns, x gathers that share 128-byte lines inside one instruction; 8 slots per lane in flight.
+        // Units are multiples of 64 slots, the row tail is zero padding.
         A s0 = 0, s1 = 0;
-        // 64 slots per warp step (2 per lane); units are multiples of 64 slots
-        long p = beg + 2 * lane;
-        for (; p + 192 < end; p += 256) {
-            T v[4][2];
-            int c[4][2];
+        for (long p = beg + lane; p < end; p += 256) {
+            T v[8];
+            int c[8];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { ld_stream2(val + p + 64 * j, v[j], pol); ld_stream2(a.long_cid + p + 64 * j, c[j], pol); }
-            A g[4][2];
+            for (int j = 0; j < 8; j++) {
+                const bool ok = p + 32 * j < end;
+                v[j] = ok ? ld_stream1(val + p + 32 * j, pol) : T(0);
+                c[j] = ok ? ld_stream1(a.long_cid + p + 32 * j, pol) : 0;
+            }
+            A g[8];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { g[j][0] = gather(x, c[j][0]); g[j][1] = gather(x, c[j][1]); }
+            for (int j = 0; j < 8; j++) g[j] = gather(x, c[j]);
 #pragma unroll
-            for (int j = 0; j < 4; j++) { s0 += to_acc(v[j][0]) * g[j][0]; s1 += to_acc(v[j][1]) * g[j][1]; }
-        }
-        for (; p < end; p += 64) {
-            T v[2];
-            int c[2];
-            ld_stream2(val + p, v, pol);
-            ld_stream2(a.long_cid + p, c, pol);
-            s0 += to_acc(v[0]) * gather(x, c[0]);
-            s1 += to_acc(v[1]) * gather(x, c[1]);
+            for (int j = 0; j < 8; j += 2) { s0 += to_acc(v[j]) * g[j]; s1 += to_acc(v[j + 1]) * g[j + 1]; }
         }
         acc = warp_sum(s0 + s1);
     }
@@ -247,10 +256,10 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
 // ------------------------------------------------------------------------------------------------
 // medium rows (row blocks)
 
-template <typename T, bool MMA>
+template <typename T, bool MMA, bool KEEP>
 __device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
 {
-    const uint64_t pol = make_stream_policy();
+    const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     const int group = cta * WARPS + (threadIdx.x >> 5); // 32 rows = 4 blocks
@@ -295,12 +304,18 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
         const T *pv = val + bp0 + 4 * r;
         const int *pc = a.reg_cid + bp0 + 4 * r;
         const int nt = (bp1 - bp0) >> 5;
-        int k = 0;
-        for (; k + 4 <= nt; k += 4) {
+        // four tiles (4 x (256-bit values + 128-bit indices)) in flight per lane; the last batch is predicated
+        for (int k = 0; k < nt; k += 4) {
             T v[4][4];
             int c[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { ld_stream4(pv + 32 * (k + j), v[j], pol); ld_stream4(pc + 32 * (k + j), c[j], pol); }
+            for (int j = 0; j < 4; j++) {
+                if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                }
+            }
             A xv[4][4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -310,14 +325,6 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
-        }
-        for (; k < nt; k++) {
-            T v[4];
-            int c[4];
-            ld_stream4(pv + 32 * k, v, pol);
-            ld_stream4(pc + 32 * k, c, pol);
-#pragma unroll
-            for (int e = 0; e < 4; e++) acc += to_acc(v[e]) * gather(x, c[e]);
         }
     }
     if (g >= a.row_block) return;
@@ -329,13 +336,76 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
     store_y<T>(a, (long)a.row_long + g, acc);
 }
 
+// Split variant for small matrices (latency-bound: fewer rows than the machine has threads).  One warp per
+// 8-row block, four lanes per row: lane 4r+q walks tiles q, q+4, ... of row r and every fourth entry of the
+// row's irregular tail; the four partial sums are folded with two shuffles.  The dependent chain is three
+// memory round trips for rows of up to 32 regular + 8 irregular entries:
+//   {blockPtr, irreg_rpt}  ->  {tile values/indices, irregular values/indices}  ->  {x gathers}
+template <typename T, bool KEEP>
+__device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, int cta)
+{
+    const StreamPol pol = make_stream_policy<KEEP>();
+    using A = typename Acc<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int b = cta * WARPS + (threadIdx.x >> 5);
+    if (b >= a.blocknum) return;
+    const int r = lane >> 2, q = lane & 3;
+    const int g = b * 8 + r;
+    const T *x = static_cast<const T *>(a.x);
+    const T *iv = static_cast<const T *>(a.irreg_val);
+    const int bp0 = __ldg(a.blockPtr + b), bp1 = __ldg(a.blockPtr + b + 1);
+    int lo = 0, hi = 0;
+    if (g < a.row_block) { lo = __ldg(a.irreg_rpt + g); hi = __ldg(a.irreg_rpt + g + 1); }
+    const T *pv = static_cast<const T *>(a.reg_val) + bp0 + 4 * r;
+    const int *pc = a.reg_cid + bp0 + 4 * r;
+    const int nt = (bp1 - bp0) >> 5;
+    A acc = 0;
+    int k = q, i = lo + q;
+    do {
+        T v[2][4], w[2];
+        int c[2][4], d[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (k + 4 * j < nt) { ld_stream4<KEEP>(pv + 32 * (k + 4 * j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + 4 * j), c[j], pol); }
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const bool ok = i + 4 * j < hi;
+            w[j] = ok ? ld_stream1(iv + i + 4 * j, pol) : T(0);
+            d[j] = ok ? ld_stream1(a.irreg_cid + i + 4 * j, pol) : 0;
+        }
+        A xv[2][4], xw[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) xw[j] = gather(x, d[j]);
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+#pragma unroll
+        for (int j = 0; j < 2; j++) acc += to_acc(w[j]) * xw[j];
+        k += 8;
+        i += 8;
+    } while (__any_sync(0xffffffffu, k < nt || i < hi));
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0 && g < a.row_block) store_y<T>(a, (long)a.row_long + g, acc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // short rows
 
-template <typename T>
+template <typename T, bool KEEP>
 __device__ __forceinline__ void short_singles(const SpmvArgs &a, int cta)
 {
-    const uint64_t pol = make_stream_policy();
+    const StreamPol pol = make_stream_policy<KEEP>();
     const T *x = static_cast<const T *>(a.x);
     const T *val = static_cast<const T *>(a.short_val) + a.s1;
     const int *cid = a.short_cid + a.s1;
@@ -363,10 +433,10 @@ __device__ __forceinline__ long paired_y(int G, long tile, int r, int h)
 }
 
 // MODE 0: 1&3 tiles   MODE 1: 3/4 rows   MODE 2: 2&2 tiles
-template <typename T, int MODE>
+template <typename T, int MODE, bool KEEP>
 __device__ __forceinline__ void short_tiles(const SpmvArgs &a, int cta)
 {
-    const uint64_t pol = make_stream_policy();
+    const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     const T *x = static_cast<const T *>(a.x);
@@ -422,16 +492,21 @@ __device__ __forceinline__ void zero_rows(const SpmvArgs &a, int cta)
     if (i < a.row_zero) store_y<T>(a, a.y0 + i, typename Acc<T>::type(0));
 }
 
-template <typename T, bool MMA_MED, bool MMA_LONG>
+// MED: 0 one lane per row (large matrices), 1 DMMA tiles, 2 four lanes per row (small matrices)
+// KEEP: the layout fits in L2, streams stay at normal L2 priority (small matrices iterated back to back)
+template <typename T, int MED, bool MMA_LONG, bool KEEP>
 __global__ void __launch_bounds__(CTA) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     const int bid = blockIdx.x;
-    if (bid < a.e_long) long_rows<T, MMA_LONG>(a, bid);
-    else if (bid < a.e_med) medium_rows<T, MMA_MED>(a, bid - a.e_long);
-    else if (bid < a.e_s1) short_singles<T>(a, bid - a.e_med);
-    else if (bid < a.e_s13) short_tiles<T, 0>(a, bid - a.e_s1);
-    else if (bid < a.e_s34) short_tiles<T, 1>(a, bid - a.e_s13);
-    else if (bid < a.e_s22) short_tiles<T, 2>(a, bid - a.e_s34);
+    if (bid < a.e_long) long_rows<T, MMA_LONG, KEEP>(a, bid);
+    else if (bid < a.e_med) {
+        if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, bid - a.e_long);
+        else medium_rows<T, MED == 1, KEEP>(a, bid - a.e_long);
+    }
+    else if (bid < a.e_s1) short_singles<T, KEEP>(a, bid - a.e_med);
+    else if (bid < a.e_s13) short_tiles<T, 0, KEEP>(a, bid - a.e_s1);
+    else if (bid < a.e_s34) short_tiles<T, 1, KEEP>(a, bid - a.e_s13);
+    else if (bid < a.e_s22) short_tiles<T, 2, KEEP>(a, bid - a.e_s34);
     else zero_rows<T>(a, bid - a.e_s22);
 }
 
@@ -474,7 +549,13 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const int tiles22 = cdiv(s.short_row_2, 2 * a.G) * (a.G / 8);
     const int per_cta = WARPS * SHORT_TILES_PER_WARP;
     a.e_long = cdiv(L.n_long_units, WARPS);
-    a.e_med = a.e_long + cdiv(s.blocknum / 4, WARPS);
+    // medium variant: AUTO follows the reference's own size switch (rowloop, src/dasp_f64.h:533-536): below
+    // 400000 medium rows the matrix cannot fill the machine with one lane per row, so rows are split 4 ways
+    int med = 0;
+    if (h->var_medium == DASP_VARIANT_MMA && !f16) med = 1;
+    else if (h->var_medium == DASP_VARIANT_SPLIT || (h->var_medium == DASP_VARIANT_AUTO && s.rowloop < 4)) med = 2;
+    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
+    a.e_med = a.e_long + (med == 2 ? cdiv(s.blocknum, WARPS) : cdiv(s.blocknum / 4, WARPS));
     a.e_s1 = a.e_med + cdiv(s.short_row_1, CTA * SINGLES_PER_THREAD);
     a.e_s13 = a.e_s1 + cdiv(tiles13, per_cta);
     a.e_s34 = a.e_s13 + cdiv(tiles34, per_cta);
@@ -482,18 +563,22 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.e_zero = a.e_s22 + cdiv(s.row_zero, CTA);
     if (a.e_zero == 0) return DASP_OK;
 
-    const bool mma_med = !f16 && h->var_medium == DASP_VARIANT_MMA;
-    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
-    if (f16)
-        spmv_kernel<__half, false, false><<<a.e_zero, CTA, 0, st>>>(a);
-    else if (mma_med && mma_long)
-        spmv_kernel<double, true, true><<<a.e_zero, CTA, 0, st>>>(a);
-    else if (mma_med)
-        spmv_kernel<double, true, false><<<a.e_zero, CTA, 0, st>>>(a);
-    else if (mma_long)
-        spmv_kernel<double, false, true><<<a.e_zero, CTA, 0, st>>>(a);
-    else
-        spmv_kernel<double, false, false><<<a.e_zero, CTA, 0, st>>>(a);
+    // B200 L2: 126 MB over two dies; keep the streams resident only when the whole working set is well below it
+    const bool keep = s.data_X <= ((int64_t)48 << 20) && med != 1 && !mma_long;
+#define DASP_LAUNCH(T, MED, ML, KEEP) spmv_kernel<T, MED, ML, KEEP><<<a.e_zero, CTA, 0, st>>>(a)
+    if (f16) {
+        if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, false, true); else DASP_LAUNCH(__half, 2, false, false); }
+        else { if (keep) DASP_LAUNCH(__half, 0, false, true); else DASP_LAUNCH(__half, 0, false, false); }
+    } else if (mma_long) {
+        if (med == 2) DASP_LAUNCH(double, 2, true, false);
+        else if (med == 1) DASP_LAUNCH(double, 1, true, false);
+        else DASP_LAUNCH(double, 0, true, false);
+    } else {
+        if (med == 2) { if (keep) DASP_LAUNCH(double, 2, false, true); else DASP_LAUNCH(double, 2, false, false); }
+        else if (med == 1) DASP_LAUNCH(double, 1, false, false);
+        else { if (keep) DASP_LAUNCH(double, 0, false, true); else DASP_LAUNCH(double, 0, false, false); }
+    }
+#undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;
 }

@@ -99,18 +99,23 @@ __global__ void plsk_len(dasp_synth_spec s, int64_t row0, int64_t rows, int *len
     len[t] = s.kind == 1 ? powerlaw_len(s, row0 + t) : skewed_len(s, row0 + t);
 }
 
-// distinct pseudo-random points of a power-of-two window: k -> lo + ((a*k + b) mod W), a odd
+// Windowed columns of a row are an ASCENDING sequence of distinct points of a window centred on the
+// row's diagonal position (CSR built from sorted input has ascending columns): the window holds
+// width = max(2*halfw, 2*len) columns, element k lands in stripe k of width/len columns at a hashed
+// offset inside the first half of the stripe (so neighbours never collide).
 __device__ inline int64_t window_col(const dasp_synth_spec &s, int64_t i, int64_t k, int len, int64_t halfw)
 {
-    int64_t W = next_pow2(2 * (halfw > len ? halfw : (int64_t)len));
-    while (W > s.n && W > 1) W >>= 1;
+    int64_t W = 2 * (halfw > len ? halfw : (int64_t)len);
+    if (W > s.n) W = s.n;
     int64_t c = (int64_t)((double)i * (double)s.n / (double)s.m);
     int64_t lo = c - W / 2;
     if (lo < 0) lo = 0;
     if (lo > s.n - W) lo = s.n - W;
-    uint64_t hr = h3(s.seed, (uint64_t)i, 0x53ull);
-    uint64_t a = (hr | 1ull), b = hr >> 17;
-    return lo + (int64_t)((a * (uint64_t)k + b) & (uint64_t)(W - 1));
+    double stripe = (double)W / (double)len; // >= 2 unless the window was clipped to n
+    double u = 0.5 * u01(h3(s.seed ^ 0x5eedull, (uint64_t)i, (uint64_t)k));
+    int64_t off = (int64_t)(((double)k + u) * stripe);
+    if (off >= W) off = W - 1;
+    return lo + off;
 }
 
 __global__ void plsk_fill(dasp_synth_spec s, int64_t row0, int64_t rows, const int *rowptr, int64_t nnz, int *colidx,
@@ -128,9 +133,13 @@ __global__ void plsk_fill(dasp_synth_spec s, int64_t row0, int64_t rows, const i
     const int len = rowptr[t + 1] - rowptr[t];
     int64_t col;
     if (s.kind == 2 && i < s.n_long) {
-        uint64_t hr = h3(s.seed, (uint64_t)i, 0x54ull);
-        uint64_t a = (hr | 1ull), b = hr >> 17;
-        col = s.band_lo + (int64_t)((a * (uint64_t)k + b) & (uint64_t)(s.band - 1));
+        // long rows of the skewed matrix: ascending, distinct, one entry per stripe of band/len columns of a
+        // band shared by all long rows (each row starts at its own hashed shift inside the first stripe)
+        double stripe = (double)s.band / (double)len;
+        double u = 0.5 * u01(h3(s.seed ^ 0x5eedull, (uint64_t)i, (uint64_t)k));
+        int64_t off = (int64_t)(((double)k + u) * stripe);
+        if (off >= s.band) off = s.band - 1;
+        col = s.band_lo + off;
     } else {
         uint64_t hk = h3(s.seed ^ 0xabcdefull, (uint64_t)i, (uint64_t)k);
         if (s.kind == 1 && hk % 10 == 0) col = (int64_t)((hk >> 8) % (uint64_t)s.n); // 10 % global

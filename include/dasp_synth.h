@@ -26,13 +26,14 @@ typedef struct dasp_synth_spec {
     uint64_t seed;
     /* stencil27: grid nx*ny*nz, natural ordering (x fastest), columns ascending */
     int nx, ny, nz;
-    /* powerlaw: L = min(floor(u^(-1/alpha)), lmax), u ~ U(0,1]; 90 % of the columns of a row are
-       distinct points of a window around i*n/m (half-width max(window, L)), 10 % uniform global */
+    /* powerlaw: L = min(floor(u^(-1/alpha)), lmax), u ~ U(0,1]; 90 % of the entries of a row are distinct
+       ASCENDING points of a window around i*n/m (half-width max(window, L), i.e. at most 50 % dense),
+       10 % are uniform global columns left at their CSR position, so rows are not sorted */
     double alpha;
     int lmax, window;
-    /* skewed: rows [0, n_long) have long_len entries, distinct, unsorted, inside one common band of
-       width band (power of two >= 2*long_len) starting at band_lo; the other rows have L uniform in
-       {1,2,3,4} with columns in a +-window window */
+    /* skewed: rows [0, n_long) have long_len entries, distinct and ascending, one per stripe of
+       band/long_len columns of one common band (width band >= 2*long_len, starting at band_lo); the
+       other rows have L uniform in {1,2,3,4} with ascending columns in a +-window window */
     int n_long, long_len;
     int64_t band_lo, band;
     /* banded-symmetric: structurally symmetric pattern, row lengths ~ mean_len */

@@ -66,7 +66,8 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         order = ref["order_rid"]
         tdt = torch.float16 if dtype == oracle.F16 else torch.float64
         dx = torch.from_numpy(x).to(cuda_device)
-        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA] if dtype == oracle.F64 else [dasp.VARIANT_AUTO]):
+        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT] if dtype == oracle.F64
+                        else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_SPLIT]):
             h.set_variant(variant, variant, variant)
             for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
                 dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
