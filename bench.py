@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
+    ap.add_argument("--power-iter", type=int, default=0, metavar="K",
+                    help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
     return ap.parse_args()
 
 
@@ -306,6 +308,13 @@ def run_ours(args):
         barrier()
         return ms
 
+    if args.power_iter > 0:
+        power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz, timed)
+        h.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     with ClockSampler(local) as clk:
         ms_local = timed(args.steps, args.warmup)
     t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
@@ -408,6 +417,78 @@ def run_ours(args):
     h.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz_rank, timed):
+    """x <- A x / ||A x||_2, K steps.  Every rank multiplies its row slab (y written straight into its slab of
+    the next x, original row order), the squared norm is all-reduced, the slab is scaled on the device and the
+    slabs are exchanged with NCCL broadcasts (slab sizes differ under the nnz-balanced partition)."""
+    import torch
+    import torch.distributed as dist
+
+    import dasp_b200
+
+    m, n = int(spec.m), int(spec.n)
+    assert m == n, "power iteration needs a square matrix"
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    xa, xb = x.clone(), torch.zeros_like(x)
+    norm2 = torch.zeros(1, dtype=torch.float64, device=dev)
+    esz = 8
+
+    def step(src, dst):
+        h.spmv_unpermuted(src, dst.data_ptr() + r0 * esz, stream)
+        dasp_b200.sumsq(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
+        if world > 1:
+            dist.all_reduce(norm2)
+        dasp_b200.scale_rsqrt(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
+        if world > 1:
+            works = [dist.broadcast(dst[cuts[p]:cuts[p + 1]], src=p, async_op=True)
+                     for p in range(world) if cuts[p + 1] > cuts[p]]
+            for w in works:
+                w.wait()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step(xa, xb)
+        xa, xb = xb, xa
+    xa.copy_(x)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.power_iter):
+        step(xa, xb)
+        xa, xb = xb, xa
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    lam = float(torch.sqrt(norm2).item())
+    chk = float(xa.double().sum().item())
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    barrier()
+    spmv_ms = torch.tensor([timed(10, 3) / 10], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(spmv_ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    step_ms = float(ms.item()) / args.power_iter
+    print(json.dumps({
+        "metric": "power_iteration_gflops", "value": 2.0 * nnz_total / (step_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+        "n_gpus": world, "steps": args.power_iter, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname + f", {args.power_iter}-step power iteration", "m": m, "nnz": nnz_total,
+                   "partition": "nnz-balanced contiguous row slabs, x replicated",
+                   "exchange": "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if world > 1 else "none (single GPU)",
+                   "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]},
+        "spmv_only_ms": float(spmv_ms.item()), "exchange_and_vector_ms": step_ms - float(spmv_ms.item()),
+        "eigenvalue_estimate": lam, "x_checksum": chk,
+        "gpu_launches": args.power_iter * (h.launches_per_spmv() + 3),
+    }), flush=True)
 
 
 def reference_kernels_leg(args, dev):

@@ -281,6 +281,18 @@ int dasp_spmv_all_f16(const char *, const void *csrValA, const int *csrRowPtrA, 
                          block_longest);
 }
 
+int dasp_sumsq(const double *d_v, int64_t count, double *d_out, void *stream)
+{
+    if ((!d_v && count > 0) || count < 0 || !d_out) { set_error("dasp_sumsq: bad argument"); return DASP_ERR_INVALID; }
+    return sumsq(d_v, count, d_out, (cudaStream_t)stream);
+}
+
+int dasp_scale_rsqrt(double *d_v, int64_t count, const double *d_norm2, void *stream)
+{
+    if ((!d_v && count > 0) || count < 0 || !d_norm2) { set_error("dasp_scale_rsqrt: bad argument"); return DASP_ERR_INVALID; }
+    return scale_by_rsqrt(d_v, count, d_norm2, (cudaStream_t)stream);
+}
+
 int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts)
 {
     if (m < 0 || !rowptr || parts < 1 || !cuts) { set_error("dasp_partition_rows: bad argument"); return DASP_ERR_INVALID; }

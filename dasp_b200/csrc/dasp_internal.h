@@ -91,4 +91,6 @@ int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, c
 // spmv.cu
 int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st);
 int launches_per_spmv(const dasp_handle *h);
+int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st);
+int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st);
 } // namespace dasp

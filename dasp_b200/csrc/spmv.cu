@@ -512,9 +512,68 @@ __global__ void __launch_bounds__(CTA) spmv_kernel(const __grid_constant__ SpmvA
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- power-iteration helpers ---------------------------------------------------------------------
+constexpr int RED_CTAS = 592; // 4 per SM
+
+__global__ void __launch_bounds__(256) sumsq_partial(const double *__restrict__ v, long n, double *__restrict__ part)
+{
+    double s = 0.0;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256L) { double t = v[i]; s += t * t; }
+    s = warp_sum(s);
+    __shared__ double w[8];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; k++) t += w[k];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) sumsq_final(const double *__restrict__ part, int n, double *__restrict__ out)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+    s = warp_sum(s);
+    __shared__ double w[8];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; k++) t += w[k];
+        *out = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_rsqrt(double *__restrict__ v, long n, const double *__restrict__ norm2)
+{
+    const double f = 1.0 / sqrt(*norm2);
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256L) v[i] *= f;
+}
+
 } // namespace
 
 int launches_per_spmv(const dasp_handle *) { return 1; }
+
+int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
+{
+    static thread_local double *scratch[64] = {nullptr};
+    int dev = 0;
+    DASP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return DASP_ERR_INVALID; }
+    if (!scratch[dev]) DASP_CUDA(cudaMalloc(&scratch[dev], sizeof(double) * RED_CTAS));
+    sumsq_partial<<<RED_CTAS, 256, 0, st>>>(d_v, (long)count, scratch[dev]);
+    sumsq_final<<<1, 256, 0, st>>>(scratch[dev], RED_CTAS, d_out);
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
+int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st)
+{
+    if (count > 0) scale_rsqrt<<<RED_CTAS * 2, 256, 0, st>>>(d_v, (long)count, d_norm2);
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
 
 int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st)
 {

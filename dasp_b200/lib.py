@@ -92,6 +92,8 @@ def load() -> C.CDLL:
         L.dasp_spmv_all_f64.argtypes = [C.c_char_p] + [vp] * 6 + [ip] * 4 + [C.c_double, ip]
         L.dasp_spmv_all_f16.argtypes = [C.c_char_p] + [vp] * 6 + [ip] * 4 + [C.c_double, ip]
         L.dasp_partition_rows.argtypes = [ip, vp, ip, vp]
+        L.dasp_sumsq.argtypes = [vp, C.c_int64, vp, vp]
+        L.dasp_scale_rsqrt.argtypes = [vp, C.c_int64, vp, vp]
         _lib = L
     return _lib
 
@@ -221,3 +223,13 @@ def partition_rows(rowptr, parts: int) -> np.ndarray:
     cuts = np.zeros(parts + 1, dtype=np.int32)
     _check(load().dasp_partition_rows(len(rp) - 1, _ptr(rp), parts, _ptr(cuts)), "dasp_partition_rows")
     return cuts
+
+
+def sumsq(d_v, count: int, d_out, stream: int = 0) -> None:
+    """*d_out = sum v[i]^2 over `count` device doubles."""
+    _check(load().dasp_sumsq(_ptr(d_v), count, _ptr(d_out), C.c_void_p(stream)), "dasp_sumsq")
+
+
+def scale_rsqrt(d_v, count: int, d_norm2, stream: int = 0) -> None:
+    """v *= 1/sqrt(*d_norm2), all on the device."""
+    _check(load().dasp_scale_rsqrt(_ptr(d_v), count, _ptr(d_norm2), C.c_void_p(stream)), "dasp_scale_rsqrt")

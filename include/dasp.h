@@ -139,6 +139,13 @@ int dasp_spmv_all_f16(const char *filename, const void *csrValA, const int *csrR
                       const int *csrColIdxA, const void *X_val, void *Y_val, int *order_rid,
                       int rowA, int colA, int nnzA, int NUM, double threshold, int block_longest);
 
+/* Vector helpers of the iterated (power-iteration) workload, x <- A x / ||A x||_2 (north_star; the
+ * reference has no iterated driver).  All pointers are device pointers, FP64 only.
+ *   dasp_sumsq:  *d_out = sum_i v[i]^2           (deterministic two-stage reduction)
+ *   dasp_scale_rsqrt: v[i] *= 1/sqrt(*d_norm2)   (d_norm2 stays on the device: no host round trip) */
+int dasp_sumsq(const double *d_v, int64_t count, double *d_out, void *stream);
+int dasp_scale_rsqrt(double *d_v, int64_t count, const double *d_norm2, void *stream);
+
 /* nnz-balanced contiguous row partition for multi-GPU runs: cut[p] = smallest i
  * with rowptr[i] >= p*nnz/parts; cuts has parts+1 entries, cut[0]=0, cut[parts]=m. rowptr: host. */
 int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts);
