@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
+    ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
     return ap.parse_args()
@@ -323,6 +324,16 @@ def run_ours(args):
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
 
+    breakdown = None
+    if args.breakdown:
+        breakdown = {}
+        for name, mask in (("long", 1), ("medium", 2), ("short", 4)):
+            h.set_category_mask(mask)
+            breakdown[name + "_ms"] = timed(max(5, args.steps // 3), 2) / max(5, args.steps // 3)
+        h.set_category_mask(15)
+        breakdown.update({"nnz_long": st["nnz_long"], "nnz_short": st["nnz_short"],
+                          "nnz_medium": st["origin_nnz_reg"] + st["nnz_irreg"]})
+
     # end to end through the C ABI with host buffers: H2D x, kernel, D2H y every step
     hx = torch.empty(n, dtype=tdt).pin_memory()
     hx.copy_(x.cpu())
@@ -376,6 +387,8 @@ def run_ours(args):
                        "device_bytes": st["device_bytes"]},
         "parity_check_rel_l2": chk,
     }
+    if breakdown:
+        line["breakdown"] = breakdown
 
     if world == 1 and not args.no_cpu and not half:
         try:

@@ -103,6 +103,7 @@ int dasp_create(dasp_handle **out, dasp_dtype dtype, int device, int m, int n, i
     dasp_handle *h = new (std::nothrow) dasp_handle();
     if (!h) { set_error("out of host memory"); return DASP_ERR_ALLOC; }
     h->device = device; h->dtype = dtype; h->threshold = threshold; h->block_longest = block_longest;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
 
     int rc = DASP_OK;
     DevicePool staging;
@@ -249,6 +250,13 @@ int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows
 {
     if (!h) { set_error("dasp_set_variant: NULL handle"); return DASP_ERR_INVALID; }
     h->var_medium = medium; h->var_long = long_rows; h->var_short = short_rows;
+    return DASP_OK;
+}
+
+int dasp_set_category_mask(dasp_handle *h, int mask)
+{
+    if (!h) { set_error("dasp_set_category_mask: NULL handle"); return DASP_ERR_INVALID; }
+    h->category_mask = mask & 15;
     return DASP_OK;
 }
 

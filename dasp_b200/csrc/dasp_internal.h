@@ -78,6 +78,8 @@ struct dasp_handle {
     int block_longest = 256;
     dasp::Layout L;
     dasp::DevicePool pool;
+    int category_mask = 15;
+    int sm_count = 0;
     dasp_variant var_medium = DASP_VARIANT_AUTO, var_long = DASP_VARIANT_AUTO, var_short = DASP_VARIANT_AUTO;
     // device staging of x / y for dasp_spmv_host (owned by pool)
     void *dx_stage = nullptr, *dy_stage = nullptr;

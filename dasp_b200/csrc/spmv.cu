@@ -56,8 +56,8 @@ struct SpmvArgs {
     int y1, y13, y34, y22, y0; // y bases (K11)
     int G;                     // 8 (f64) / 32 (f16)
     int row_zero;
-    // exclusive block-range ends
-    int e_long, e_med, e_s1, e_s13, e_s34, e_s22, e_zero;
+    int e[7];      // exclusive CTA-range end of category k (long, medium, singles, 1&3, 3/4, 2&2, zero)
+    long items[7]; // warp-level work items of category k
 };
 
 template <typename T> struct Acc;
@@ -170,13 +170,13 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 // long rows
 
 template <typename T, bool MMA, bool KEEP>
-__device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void long_rows(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
-    const int u = cta * WARPS + (threadIdx.x >> 5);
-    if (u >= a.n_units) return;
+    if (w >= a.n_units) return;
+    const int u = (int)w;
     const T *x = static_cast<const T *>(a.x);
     const int row = __ldg(a.unit_row + u);
     const int first = __ldg(a.unit_first + row), nunits = __ldg(a.unit_first + row + 1) - first;
@@ -209,23 +209,36 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
         acc = (A)warp_sum(d);
     } else {
         // 32 slots per warp load (lane, lane+32, ...): fully coalesced value/index streams and, for ascending
-        // columns, x gathers that share 128-byte lines inside one instruction; 8 slots per lane in flight.
-        // Units are multiples of 64 slots, the row tail is zero padding.
+        // columns, x gathers that share 128-byte lines inside one instruction.  Software pipelined by hand (the
+        // asm loads keep program order): the streams of batch i+1 are in flight while the gathers of batch i
+        // are pending.  Units are multiples of 64 slots, the row tail is zero padding; loads past `end` are
+        // predicated off.
+        constexpr int LB = 4; // slots per lane per batch = 128 slots per warp
         A s0 = 0, s1 = 0;
-        for (long p = beg + lane; p < end; p += 256) {
-            T v[8];
-            int c[8];
+        T v0[LB], v1[LB];
+        int c0[LB], c1[LB];
+        auto load = [&](T(&v)[LB], int(&c)[LB], long q) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool ok = p + 32 * j < end;
-                v[j] = ok ? ld_stream1(val + p + 32 * j, pol) : T(0);
-                c[j] = ok ? ld_stream1(a.long_cid + p + 32 * j, pol) : 0;
+            for (int j = 0; j < LB; j++) {
+                const bool ok = q + 32 * j < end;
+                v[j] = ok ? ld_stream1(val + q + 32 * j, pol) : T(0);
+                c[j] = ok ? ld_stream1(a.long_cid + q + 32 * j, pol) : 0;
             }
-            A g[8];
+        };
+        auto consume = [&](const T(&v)[LB], const int(&c)[LB]) {
+            A g[LB];
 #pragma unroll
-            for (int j = 0; j < 8; j++) g[j] = gather(x, c[j]);
+            for (int j = 0; j < LB; j++) g[j] = gather(x, c[j]);
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) { s0 += to_acc(v[j]) * g[j]; s1 += to_acc(v[j + 1]) * g[j + 1]; }
+            for (int j = 0; j < LB; j += 2) { s0 += to_acc(v[j]) * g[j]; s1 += to_acc(v[j + 1]) * g[j + 1]; }
+        };
+        long p = beg + lane;
+        load(v0, c0, p);
+        for (; p < end; p += 64 * LB) {
+            load(v1, c1, p + 32 * LB);
+            consume(v0, c0);
+            load(v0, c0, p + 64 * LB);
+            consume(v1, c1);
         }
         acc = warp_sum(s0 + s1);
     }
@@ -257,13 +270,13 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, int cta)
 // medium rows (row blocks)
 
 template <typename T, bool MMA, bool KEEP>
-__device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
-    const int group = cta * WARPS + (threadIdx.x >> 5); // 32 rows = 4 blocks
-    if (group * 4 >= a.blocknum) return;
+    if (w * 4 >= a.blocknum) return;
+    const int group = (int)w; // 32 rows = 4 blocks
     const T *x = static_cast<const T *>(a.x);
     const T *val = static_cast<const T *>(a.reg_val);
     const int g = group * 32 + lane;
@@ -342,13 +355,13 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, int cta)
 // memory round trips for rows of up to 32 regular + 8 irregular entries:
 //   {blockPtr, irreg_rpt}  ->  {tile values/indices, irregular values/indices}  ->  {x gathers}
 template <typename T, bool KEEP>
-__device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
-    const int b = cta * WARPS + (threadIdx.x >> 5);
-    if (b >= a.blocknum) return;
+    if (w >= a.blocknum) return;
+    const int b = (int)w;
     const int r = lane >> 2, q = lane & 3;
     const int g = b * 8 + r;
     const T *x = static_cast<const T *>(a.x);
@@ -403,23 +416,23 @@ __device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, int cta)
 // short rows
 
 template <typename T, bool KEEP>
-__device__ __forceinline__ void short_singles(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void short_singles(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     const T *x = static_cast<const T *>(a.x);
     const T *val = static_cast<const T *>(a.short_val) + a.s1;
     const int *cid = a.short_cid + a.s1;
-    const long base = (long)cta * CTA * SINGLES_PER_THREAD + threadIdx.x;
+    const long base = w * 32 * SINGLES_PER_THREAD + (threadIdx.x & 31);
     T v[SINGLES_PER_THREAD];
     int c[SINGLES_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < SINGLES_PER_THREAD; j++) {
-        long i = base + j * CTA;
+        long i = base + j * 32;
         if (i < a.n1) { v[j] = ld_stream1(val + i, pol); c[j] = ld_stream1(cid + i, pol); }
     }
 #pragma unroll
     for (int j = 0; j < SINGLES_PER_THREAD; j++) {
-        long i = base + j * CTA;
+        long i = base + j * 32;
         if (i < a.n1) store_y<T>(a, a.y1 + i, to_acc(v[j]) * gather(x, c[j]));
     }
 }
@@ -434,7 +447,7 @@ __device__ __forceinline__ long paired_y(int G, long tile, int r, int h)
 
 // MODE 0: 1&3 tiles   MODE 1: 3/4 rows   MODE 2: 2&2 tiles
 template <typename T, int MODE, bool KEEP>
-__device__ __forceinline__ void short_tiles(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
@@ -444,7 +457,7 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, int cta)
     const long nrows = MODE == 0 ? a.c13 : (MODE == 1 ? a.n34 : a.n2); // rows (pairs for MODE 0)
     const T *val = static_cast<const T *>(a.short_val) + sbase;
     const int *cid = a.short_cid + sbase;
-    const long tile0 = ((long)cta * WARPS + (threadIdx.x >> 5)) * SHORT_TILES_PER_WARP;
+    const long tile0 = w * SHORT_TILES_PER_WARP;
     // 2&2 packs 2G rows per G/8 tiles (16 per tile in FP64, 64 per 4 tiles in FP16)
     const long tiles_avail = MODE == 2 ? ((nrows + 2 * a.G - 1) / (2 * a.G)) * (a.G >> 3) : (nrows + 7) / 8;
     A p[SHORT_TILES_PER_WARP];
@@ -486,28 +499,42 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, int cta)
 }
 
 template <typename T>
-__device__ __forceinline__ void zero_rows(const SpmvArgs &a, int cta)
+__device__ __forceinline__ void zero_rows(const SpmvArgs &a, long w)
 {
-    long i = (long)cta * CTA + threadIdx.x;
+    long i = w * 32 + (threadIdx.x & 31);
     if (i < a.row_zero) store_y<T>(a, a.y0 + i, typename Acc<T>::type(0));
 }
 
 // MED: 0 one lane per row (large matrices), 1 DMMA tiles, 2 four lanes per row (small matrices)
 // KEEP: the layout fits in L2, streams stay at normal L2 priority (small matrices iterated back to back)
 template <typename T, int MED, bool MMA_LONG, bool KEEP>
-__global__ void __launch_bounds__(CTA) spmv_kernel(const __grid_constant__ SpmvArgs a)
+__device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w)
 {
-    const int bid = blockIdx.x;
-    if (bid < a.e_long) long_rows<T, MMA_LONG, KEEP>(a, bid);
-    else if (bid < a.e_med) {
-        if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, bid - a.e_long);
-        else medium_rows<T, MED == 1, KEEP>(a, bid - a.e_long);
+    switch (cat) {
+    case 0: long_rows<T, MMA_LONG, KEEP>(a, w); break;
+    case 1:
+        if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, w);
+        else medium_rows<T, MED == 1, KEEP>(a, w);
+        break;
+    case 2: short_singles<T, KEEP>(a, w); break;
+    case 3: short_tiles<T, 0, KEEP>(a, w); break;
+    case 4: short_tiles<T, 1, KEEP>(a, w); break;
+    case 5: short_tiles<T, 2, KEEP>(a, w); break;
+    default: zero_rows<T>(a, w); break;
     }
-    else if (bid < a.e_s1) short_singles<T, KEEP>(a, bid - a.e_med);
-    else if (bid < a.e_s13) short_tiles<T, 0, KEEP>(a, bid - a.e_s1);
-    else if (bid < a.e_s34) short_tiles<T, 1, KEEP>(a, bid - a.e_s13);
-    else if (bid < a.e_s22) short_tiles<T, 2, KEEP>(a, bid - a.e_s34);
-    else zero_rows<T>(a, bid - a.e_s22);
+}
+
+// One warp per work item; the block index selects the category (grid = sum of the per-category CTA counts).
+template <typename T, int MED, bool MMA_LONG, bool KEEP>
+__global__ void __launch_bounds__(CTA, KEEP ? 1 : 6) spmv_kernel(const __grid_constant__ SpmvArgs a)
+{
+    const int bid = blockIdx.x, warp = threadIdx.x >> 5;
+    int cat = 0, first = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (bid >= a.e[k]) { cat = k + 1; first = a.e[k]; }
+    const int local = bid - first;
+    run_category<T, MED, MMA_LONG, KEEP>(a, cat, (long)local * WARPS + warp);
 }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -606,25 +633,46 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
 
     const int tiles13 = cdiv(s.common_13, 8), tiles34 = cdiv(s.short_row_34, 8);
     const int tiles22 = cdiv(s.short_row_2, 2 * a.G) * (a.G / 8);
-    const int per_cta = WARPS * SHORT_TILES_PER_WARP;
-    a.e_long = cdiv(L.n_long_units, WARPS);
-    // medium variant: AUTO follows the reference's own size switch (rowloop, src/dasp_f64.h:533-536): below
-    // 400000 medium rows the matrix cannot fill the machine with one lane per row, so rows are split 4 ways
+    const int cm = h->category_mask;
+    const int on_long = cm & 1, on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1, on_zero = (cm >> 3) & 1;
+    // medium variant: AUTO = one lane per row.  The 4-lanes-per-row split (the analogue of the reference's
+    // rowloop=1 geometry for small matrices, src/dasp_f64.h:533-536) and the DMMA tiles are kept as measured
+    // alternatives: both lose on B200 (profiles/r01/variants.md).
+    const bool small = s.data_X <= ((int64_t)48 << 20); // B200 L2: 126 MB over two dies
     int med = 0;
     if (h->var_medium == DASP_VARIANT_MMA && !f16) med = 1;
-    else if (h->var_medium == DASP_VARIANT_SPLIT || (h->var_medium == DASP_VARIANT_AUTO && s.rowloop < 4)) med = 2;
+    else if (h->var_medium == DASP_VARIANT_SPLIT) med = 2;
     const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
-    a.e_med = a.e_long + (med == 2 ? cdiv(s.blocknum, WARPS) : cdiv(s.blocknum / 4, WARPS));
-    a.e_s1 = a.e_med + cdiv(s.short_row_1, CTA * SINGLES_PER_THREAD);
-    a.e_s13 = a.e_s1 + cdiv(tiles13, per_cta);
-    a.e_s34 = a.e_s13 + cdiv(tiles34, per_cta);
-    a.e_s22 = a.e_s34 + cdiv(tiles22, per_cta);
-    a.e_zero = a.e_s22 + cdiv(s.row_zero, CTA);
-    if (a.e_zero == 0) return DASP_OK;
+    a.items[0] = on_long * (long)L.n_long_units;
+    a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);
+    a.items[2] = on_short * (long)cdiv(s.short_row_1, 32 * SINGLES_PER_THREAD);
+    a.items[3] = on_short * (long)cdiv(tiles13, SHORT_TILES_PER_WARP);
+    a.items[4] = on_short * (long)cdiv(tiles34, SHORT_TILES_PER_WARP);
+    a.items[5] = on_short * (long)cdiv(tiles22, SHORT_TILES_PER_WARP);
+    a.items[6] = on_zero * (long)cdiv(s.row_zero, 32);
+    long total_items = 0;
+    int acc_ctas = 0;
+    for (int k = 0; k < 7; k++) {
+        acc_ctas += cdiv(a.items[k], WARPS);
+        a.e[k] = acc_ctas;
+        total_items += a.items[k];
+    }
+    if (total_items == 0) return DASP_OK;
+    const int grid = a.e[6];
 
-    // B200 L2: 126 MB over two dies; keep the streams resident only when the whole working set is well below it
-    const bool keep = s.data_X <= ((int64_t)48 << 20) && med != 1 && !mma_long;
-#define DASP_LAUNCH(T, MED, ML, KEEP) spmv_kernel<T, MED, ML, KEEP><<<a.e_zero, CTA, 0, st>>>(a)
+    // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
+    const bool keep = small && med != 1 && !mma_long;
+    // the kernels use no shared memory: ask for the whole unified array as L1 (x gathers live there), as the
+    // reference does (src/dasp_f64.h:1280-1283)
+#define DASP_LAUNCH(T, MED, ML, KEEP)                                                                              \
+    do {                                                                                                           \
+        static bool carved = false;                                                                                \
+        if (!carved) {                                                                                             \
+            cudaFuncSetAttribute(spmv_kernel<T, MED, ML, KEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
+            carved = true;                                                                                         \
+        }                                                                                                          \
+        spmv_kernel<T, MED, ML, KEEP><<<grid, CTA, 0, st>>>(a);                                                    \
+    } while (0)
     if (f16) {
         if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, false, true); else DASP_LAUNCH(__half, 2, false, false); }
         else { if (keep) DASP_LAUNCH(__half, 0, false, true); else DASP_LAUNCH(__half, 0, false, false); }

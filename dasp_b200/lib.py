@@ -85,6 +85,7 @@ def load() -> C.CDLL:
         L.dasp_export.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.dasp_set_variant.argtypes = [vp, ip, ip, ip]
         L.dasp_launches_per_spmv.argtypes = [vp]
+        L.dasp_set_category_mask.argtypes = [vp, ip]
         L.dasp_destroy.argtypes = [vp]
         L.dasp_strerror.restype = C.c_char_p
         L.dasp_strerror.argtypes = [ip]
@@ -186,6 +187,10 @@ class Dasp:
 
     def set_variant(self, medium: int = 0, long_rows: int = 0, short_rows: int = 0) -> None:
         _check(load().dasp_set_variant(self._h, medium, long_rows, short_rows), "dasp_set_variant")
+
+    def set_category_mask(self, mask: int) -> None:
+        """Profiling aid: bit 0 long, 1 medium, 2 short, 3 empty rows."""
+        _check(load().dasp_set_category_mask(self._h, mask), "dasp_set_category_mask")
 
     def launches_per_spmv(self) -> int:
         return load().dasp_launches_per_spmv(self._h)

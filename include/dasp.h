@@ -121,6 +121,10 @@ int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t 
 
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 
+/* Profiling aid: restrict dasp_spmv to some row categories (bit 0 long, bit 1 medium, bit 2 short,
+ * bit 3 empty rows; default 15 = all).  y entries of disabled categories are left untouched. */
+int dasp_set_category_mask(dasp_handle *h, int mask);
+
 /* number of kernel launches one dasp_spmv issues (for launch accounting) */
 int dasp_launches_per_spmv(const dasp_handle *h);
 
