@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--grid", type=int, default=256, help="c4: stencil grid edge")
     ap.add_argument("--scale", type=float, default=1.0, help="c3/c5: fraction of the named size")
-    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split", "tma"])
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
@@ -250,8 +250,8 @@ def run_ours(args):
     h = dasp_b200.Dasp(dtype, r1 - r0, n, rp, ci, v, device=local, nnz=nnz)
     create_s = time.perf_counter() - t0
     st = h.stats()
-    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3}[args.variant]
-    h.set_variant(var, var, var)
+    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3, "tma": 4}[args.variant]
+    h.set_variant(0 if var == 4 else var, 0 if var == 3 else var, 0)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)

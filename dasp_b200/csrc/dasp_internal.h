@@ -62,7 +62,8 @@ struct Layout {
     int *short_cid = nullptr;
     // ---- derived launch data of this implementation (not part of the reference layout) ----
     int n_long_units = 0;
-    int *long_unit_row = nullptr;   // [n_long_units] long row of each unit
+    int *long_unit_row = nullptr;   // [n_long_units] long row of each unit (execution order)
+    int *long_unit_chunk = nullptr; // [n_long_units] which chunk of that row
     int *long_unit_first = nullptr; // [row_long+1]  first unit of each long row
     void *long_partial = nullptr;   // [n_long_units] double (f64) / float (f16) partial sums
     unsigned *long_done = nullptr;  // [row_long] arrival counters (self-resetting)

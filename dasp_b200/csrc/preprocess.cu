@@ -159,10 +159,28 @@ __global__ void long_warps(const int *__restrict__ rowptr, const int *__restrict
     upr[i] = (w + LONG_UNIT_WARPS - 1) / LONG_UNIT_WARPS;
 }
 
-__global__ void fill_long_units(const int *__restrict__ unit_first, int row_long, int *__restrict__ unit_row)
+// Execution order of the long-row work units.  Inside every group of 8 consecutive long rows the units are
+// enumerated chunk-major (chunk c of rows 8g..8g+7, then chunk c+1, ...), so the 8 warps of one CTA work on the
+// SAME slot range of 8 neighbouring long rows: rows that are long because they touch the same dense column range
+// (borders, constraints) then share their x sectors through that SM's L1.  Rows with fewer chunks simply drop out.
+__global__ void fill_long_units(const int *__restrict__ unit_first, int row_long, int *__restrict__ unit_row,
+                                int *__restrict__ unit_chunk)
 {
-    int i = blockIdx.x;
-    for (int u = unit_first[i] + threadIdx.x; u < unit_first[i + 1]; u += blockDim.x) unit_row[u] = i;
+    const int r0 = blockIdx.x * 8;
+    int n[8], base = unit_first[r0], most = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        n[r] = (r0 + r < row_long) ? unit_first[r0 + r + 1] - unit_first[r0 + r] : 0;
+        most = max(most, n[r]);
+    }
+    for (int c = threadIdx.x; c < most; c += blockDim.x) {
+        int pos = base;
+#pragma unroll
+        for (int r = 0; r < 8; r++) pos += min(n[r], c);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (n[r] > c) { unit_row[pos] = r0 + r; unit_chunk[pos] = c; pos++; }
+    }
 }
 
 template <typename T>
@@ -456,6 +474,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(pool.alloc((void **)&L.short_cid, sizeof(int) * (size_t)s.fill0_nnz_short));
     DASP_TRY(pool.alloc((void **)&L.order_rid, sizeof(int) * (size_t)m));
     DASP_TRY(pool.alloc((void **)&L.long_unit_row, sizeof(int) * (size_t)L.n_long_units));
+    DASP_TRY(pool.alloc((void **)&L.long_unit_chunk, sizeof(int) * (size_t)L.n_long_units));
     DASP_TRY(pool.alloc(&L.long_partial, 8 * (size_t)L.n_long_units));
     DASP_TRY(pool.alloc((void **)&L.long_done, sizeof(unsigned) * (size_t)cl));
     const int ngroups = ceil_div(cm, 32);
@@ -487,7 +506,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         if (per_row > 64) per_row = 64;
         pack_long<T><<<dim3(cl, per_row), 256, 0, st>>>(rowptr, colidx, val, cat_rid + seg[CAT_LONG], L.long_rpt_new, LONGW,
                                                         (T *)L.long_val, L.long_cid);
-        fill_long_units<<<cl, 64, 0, st>>>(L.long_unit_first, cl, L.long_unit_row);
+        fill_long_units<<<(cl + 7) / 8, 128, 0, st>>>(L.long_unit_first, cl, L.long_unit_row, L.long_unit_chunk);
     }
     // ---- P13/P14: medium rows ----
     if (cm > 0) {

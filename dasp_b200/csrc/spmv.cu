@@ -37,7 +37,7 @@ struct SpmvArgs {
     const int *scatter; // nullptr: permuted order
     // long
     const void *long_val;
-    const int *long_cid, *long_rpt_new, *unit_row, *unit_first;
+    const int *long_cid, *long_rpt_new, *unit_row, *unit_chunk, *unit_first;
     void *partial;
     unsigned *done;
     int n_units, longw;
@@ -142,6 +142,35 @@ __device__ __forceinline__ int ld_stream1(const int *p, const StreamPol &pol)
     return v;
 }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP) and mbarrier helpers for the long-row stream ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+constexpr int TMA_STAGES = 3;          // stages of the per-warp ring
+constexpr int TMA_STAGE_SLOTS = 128;   // slots per stage: 1 KB of FP64 values + 512 B of indices
+constexpr int TMA_STAGE_BYTES = TMA_STAGE_SLOTS * 12;
+constexpr int TMA_WARP_BYTES = TMA_STAGES * TMA_STAGE_BYTES;
+constexpr int TMA_SMEM_BYTES = WARPS * TMA_WARP_BYTES + WARPS * TMA_STAGES * 8;
+
 // x gathers: read-only path, allocate in L1 (neighbouring rows reuse the same entries)
 template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c) { return to_acc(__ldg(x + c)); }
 
@@ -169,19 +198,21 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 // ------------------------------------------------------------------------------------------------
 // long rows
 
-template <typename T, bool MMA, bool KEEP>
-__device__ __forceinline__ void long_rows(const SpmvArgs &a, long w)
+// LONGV: 0 CUDA-core with register-staged loads, 1 DMMA, 2 CUDA-core fed by a per-warp TMA bulk-copy ring
+template <typename T, int LONGV, bool KEEP>
+__device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned char *smem)
 {
+    constexpr bool MMA = LONGV == 1;
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     if (w >= a.n_units) return;
     const int u = (int)w;
     const T *x = static_cast<const T *>(a.x);
-    const int row = __ldg(a.unit_row + u);
+    const int row = __ldg(a.unit_row + u), chunk = __ldg(a.unit_chunk + u);
     const int first = __ldg(a.unit_first + row), nunits = __ldg(a.unit_first + row + 1) - first;
     const long row_beg = (long)__ldg(a.long_rpt_new + row) * a.longw, row_end = (long)__ldg(a.long_rpt_new + row + 1) * a.longw;
-    const long beg = row_beg + (long)(u - first) * LONG_UNIT_WARPS * a.longw;
+    const long beg = row_beg + (long)chunk * LONG_UNIT_WARPS * a.longw;
     const long end = min(beg + (long)LONG_UNIT_WARPS * a.longw, row_end);
     const T *val = static_cast<const T *>(a.long_val);
     A acc = 0;
@@ -207,6 +238,56 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w)
         const int n0 = 2 * (lane & 3);
         double d = (n0 == grp ? c[0] : 0.0) + (n0 + 1 == grp ? c[1] : 0.0);
         acc = (A)warp_sum(d);
+    } else if constexpr (LONGV == 2) {
+        // The dense value/index streams of the unit are moved by TMA 1-D bulk copies into a 3-stage shared-memory
+        // ring owned by this warp (lane 0 is the producer, one mbarrier per stage); the lanes read their slots from
+        // shared memory (conflict-free 8-byte / 4-byte accesses) and only the x gathers go through L1.  Bytes in
+        // flight per warp: 3 x 1.5 KB without holding a single register.
+        const int warp = threadIdx.x >> 5;
+        unsigned char *ring = smem + warp * TMA_WARP_BYTES;
+        const uint32_t bar0 = smem_u32(smem + WARPS * TMA_WARP_BYTES + warp * TMA_STAGES * 8);
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < TMA_STAGES; st++) mbar_init(bar0 + 8 * st, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        const int nstage = (int)((end - beg + TMA_STAGE_SLOTS - 1) / TMA_STAGE_SLOTS);
+        auto issue = [&](int it) { // lane 0 only
+            const int st = it % TMA_STAGES;
+            const long q = beg + (long)it * TMA_STAGE_SLOTS;
+            const uint32_t n = (uint32_t)min((long)TMA_STAGE_SLOTS, end - q);
+            const uint32_t dst = smem_u32(ring + st * TMA_STAGE_BYTES);
+            mbar_expect_tx(bar0 + 8 * st, n * (uint32_t)(sizeof(T) + 4));
+            bulk_g2s(dst, val + q, n * (uint32_t)sizeof(T), bar0 + 8 * st, pol.desc);
+            bulk_g2s(dst + TMA_STAGE_SLOTS * 8, a.long_cid + q, n * 4u, bar0 + 8 * st, pol.desc);
+        };
+        if (lane == 0)
+            for (int it = 0; it < TMA_STAGES && it < nstage; it++) issue(it);
+        A s0 = 0, s1 = 0;
+        for (int it = 0; it < nstage; it++) {
+            const int st = it % TMA_STAGES;
+            mbar_wait(bar0 + 8 * st, (uint32_t)((it / TMA_STAGES) & 1));
+            const T *sv = reinterpret_cast<const T *>(ring + st * TMA_STAGE_BYTES);
+            const int *sc = reinterpret_cast<const int *>(ring + st * TMA_STAGE_BYTES + TMA_STAGE_SLOTS * 8);
+            const int n = (int)min((long)TMA_STAGE_SLOTS, end - (beg + (long)it * TMA_STAGE_SLOTS));
+            T v[4];
+            int c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool ok = lane + 32 * j < n;
+                v[j] = ok ? sv[lane + 32 * j] : T(0);
+                c[j] = ok ? sc[lane + 32 * j] : 0;
+            }
+            __syncwarp(); // every lane has its slots in registers: the stage may be refilled
+            if (lane == 0 && it + TMA_STAGES < nstage) issue(it + TMA_STAGES);
+            A g[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) g[j] = gather(x, c[j]);
+            s0 += to_acc(v[0]) * g[0] + to_acc(v[2]) * g[2];
+            s1 += to_acc(v[1]) * g[1] + to_acc(v[3]) * g[3];
+        }
+        acc = warp_sum(s0 + s1);
     } else {
         // 32 slots per warp load (lane, lane+32, ...): fully coalesced value/index streams and, for ascending
         // columns, x gathers that share 128-byte lines inside one instruction.  Software pipelined by hand (the
@@ -250,7 +331,7 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w)
     A *partial = static_cast<A *>(a.partial);
     unsigned prev = 0;
     if (lane == 0) {
-        __stcg(partial + u, acc);
+        __stcg(partial + first + chunk, acc);
         __threadfence();
         prev = atomicAdd(a.done + row, 1u);
     }
@@ -507,11 +588,11 @@ __device__ __forceinline__ void zero_rows(const SpmvArgs &a, long w)
 
 // MED: 0 one lane per row (large matrices), 1 DMMA tiles, 2 four lanes per row (small matrices)
 // KEEP: the layout fits in L2, streams stay at normal L2 priority (small matrices iterated back to back)
-template <typename T, int MED, bool MMA_LONG, bool KEEP>
-__device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w)
+template <typename T, int MED, int LONGV, bool KEEP>
+__device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w, unsigned char *smem)
 {
     switch (cat) {
-    case 0: long_rows<T, MMA_LONG, KEEP>(a, w); break;
+    case 0: long_rows<T, LONGV, KEEP>(a, w, smem); break;
     case 1:
         if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, w);
         else medium_rows<T, MED == 1, KEEP>(a, w);
@@ -525,16 +606,17 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w)
 }
 
 // One warp per work item; the block index selects the category (grid = sum of the per-category CTA counts).
-template <typename T, int MED, bool MMA_LONG, bool KEEP>
+template <typename T, int MED, int LONGV, bool KEEP>
 __global__ void __launch_bounds__(CTA, KEEP ? 1 : 6) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
+    extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
     int cat = 0, first = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++)
         if (bid >= a.e[k]) { cat = k + 1; first = a.e[k]; }
     const int local = bid - first;
-    run_category<T, MED, MMA_LONG, KEEP>(a, cat, (long)local * WARPS + warp);
+    run_category<T, MED, LONGV, KEEP>(a, cat, (long)local * WARPS + warp, dyn_smem);
 }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -610,7 +692,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     SpmvArgs a{};
     a.x = d_x; a.y = d_y; a.scatter = scatter;
     a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
-    a.unit_row = L.long_unit_row; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
+    a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
     a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
     a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
@@ -643,6 +725,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     if (h->var_medium == DASP_VARIANT_MMA && !f16) med = 1;
     else if (h->var_medium == DASP_VARIANT_SPLIT) med = 2;
     const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
+    const bool tma_long = h->var_long == DASP_VARIANT_TMA;
     a.items[0] = on_long * (long)L.n_long_units;
     a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);
     a.items[2] = on_short * (long)cdiv(s.short_row_1, 32 * SINGLES_PER_THREAD);
@@ -661,29 +744,32 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const int grid = a.e[6];
 
     // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
-    const bool keep = small && med != 1 && !mma_long;
-    // the kernels use no shared memory: ask for the whole unified array as L1 (x gathers live there), as the
+    const bool keep = small && med != 1 && !mma_long && !tma_long;
+    // the kernels that use no shared memory ask for the whole unified array as L1 (x gathers live there), as the
     // reference does (src/dasp_f64.h:1280-1283)
-#define DASP_LAUNCH(T, MED, ML, KEEP)                                                                              \
+#define DASP_LAUNCH(T, MED, LV, KEEP)                                                                              \
     do {                                                                                                           \
         static bool carved = false;                                                                                \
-        if (!carved) {                                                                                             \
-            cudaFuncSetAttribute(spmv_kernel<T, MED, ML, KEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
+        if (!carved && LV != 2) {                                                                                  \
+            cudaFuncSetAttribute(spmv_kernel<T, MED, LV, KEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
             carved = true;                                                                                         \
         }                                                                                                          \
-        spmv_kernel<T, MED, ML, KEEP><<<grid, CTA, 0, st>>>(a);                                                    \
+        spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                         \
     } while (0)
     if (f16) {
-        if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, false, true); else DASP_LAUNCH(__half, 2, false, false); }
-        else { if (keep) DASP_LAUNCH(__half, 0, false, true); else DASP_LAUNCH(__half, 0, false, false); }
+        if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
+        else if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, 0, true); else DASP_LAUNCH(__half, 2, 0, false); }
+        else { if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
+    } else if (tma_long) {
+        DASP_LAUNCH(double, 0, 2, false);
     } else if (mma_long) {
-        if (med == 2) DASP_LAUNCH(double, 2, true, false);
-        else if (med == 1) DASP_LAUNCH(double, 1, true, false);
-        else DASP_LAUNCH(double, 0, true, false);
+        if (med == 2) DASP_LAUNCH(double, 2, 1, false);
+        else if (med == 1) DASP_LAUNCH(double, 1, 1, false);
+        else DASP_LAUNCH(double, 0, 1, false);
     } else {
-        if (med == 2) { if (keep) DASP_LAUNCH(double, 2, false, true); else DASP_LAUNCH(double, 2, false, false); }
-        else if (med == 1) DASP_LAUNCH(double, 1, false, false);
-        else { if (keep) DASP_LAUNCH(double, 0, false, true); else DASP_LAUNCH(double, 0, false, false); }
+        if (med == 2) { if (keep) DASP_LAUNCH(double, 2, 0, true); else DASP_LAUNCH(double, 2, 0, false); }
+        else if (med == 1) DASP_LAUNCH(double, 1, 0, false);
+        else { if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
     }
 #undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());

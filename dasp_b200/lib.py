@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 DASP_F64, DASP_F16 = 0, 1
-VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA = 0, 1, 2, 3, 4
 
 _STATS_INT = [
     "dtype", "m", "n", "nnz",  # nnz is int64, handled below

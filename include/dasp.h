@@ -51,7 +51,8 @@ typedef enum {
     DASP_VARIANT_AUTO = 0,
     DASP_VARIANT_CUDA_CORE = 1, /* per-lane 4-wide dot over the 8x4 tiles, 256/128-bit loads */
     DASP_VARIANT_MMA = 2,       /* mma.sync m8n8k4.f64 (DMMA) on the same tiles, as the reference does */
-    DASP_VARIANT_SPLIT = 3      /* medium rows only: CUDA-core, four lanes per row (small, latency-bound matrices) */
+    DASP_VARIANT_SPLIT = 3,     /* medium rows only: CUDA-core, four lanes per row (small, latency-bound matrices) */
+    DASP_VARIANT_TMA = 4        /* long rows only: CUDA-core fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier ring) */
 } dasp_variant;
 
 /* The reference's locals that describe the layout (the 18 structure columns of its CSV record,
