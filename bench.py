@@ -131,6 +131,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
+    p = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    key = {"c4": f"c4:{args.grid}", "c3": f"c3:{args.scale}", "c5": f"c5:{args.scale}"}.get(args.workload)
+    e = json.load(open(p)).get(key)
+    return e["traffic_bytes"] if e and int(os.environ.get("WORLD_SIZE", "1")) == 1 else None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -375,7 +385,7 @@ def run_ours(args):
         "hbm_gbs": b_alg_total / (ms_step * 1e-3) / 1e9,
         "hbm_frac_of_8tbs": b_alg_total / (ms_step * 1e-3) / 8e12 / world,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "kernel": "spmv_kernel (fused, rank 0 slab)", "peak_source": peak_src,
+                     "traffic": ncu_traffic(args), "kernel": "spmv_kernel (fused, rank 0 slab)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b_alg_rank},
         "gpu_launches": args.steps * h.launches_per_spmv(),
         "clocks": clk.summary(),

@@ -108,21 +108,6 @@ template <bool KEEP> __device__ __forceinline__ void ld_stream4(const int *p, in
     asm volatile(DASP_LD_HINT ".v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p), "l"(pol.desc));
 }
-__device__ __forceinline__ void ld_stream2(const double *p, double (&v)[2], const StreamPol &pol)
-{
-    asm volatile(DASP_LD_HINT ".v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol.desc));
-}
-__device__ __forceinline__ void ld_stream2(const __half *p, __half (&v)[2], const StreamPol &pol)
-{
-    unsigned a;
-    asm volatile(DASP_LD_HINT ".u32 %0, [%1], %2;" : "=r"(a) : "l"(p), "l"(pol.desc));
-    __half2 h = *reinterpret_cast<__half2 *>(&a);
-    v[0] = __low2half(h); v[1] = __high2half(h);
-}
-__device__ __forceinline__ void ld_stream2(const int *p, int (&v)[2], const StreamPol &pol)
-{
-    asm volatile(DASP_LD_HINT ".v2.s32 {%0,%1}, [%2], %3;" : "=r"(v[0]), "=r"(v[1]) : "l"(p), "l"(pol.desc));
-}
 __device__ __forceinline__ double ld_stream1(const double *p, const StreamPol &pol)
 {
     double v;
