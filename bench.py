@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
+    ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
@@ -436,8 +437,12 @@ def run_ours(args):
             sec["ref_dasp_sm100a"] = {"error": repr(e)}
         line["secondary"] = sec
 
-    print(json.dumps(line), flush=True)
     h.close()
+    if world == 1 and args.workload == "c4" and not args.no_others and not args.no_secondary:
+        del x, y
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs(args, dev)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -512,6 +517,62 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         "eigenvalue_estimate": lam, "x_checksum": chk,
         "gpu_launches": args.power_iter * (h.launches_per_spmv() + 3),
     }), flush=True)
+
+
+def other_configs(args, dev):
+    """Short measurements of the remaining BASELINE.json configurations (1 GPU), same protocol as the headline:
+    generate on the device, dasp_create, bounded parity check against the serial CSR oracle, K back-to-back
+    launches timed with CUDA events from C."""
+    import copy
+
+    import torch
+
+    import dasp_b200
+    import oracle
+    from dasp_b200 import synth
+
+    out = {}
+    for w in ("c1", "c2", "c3", "c5"):
+        a = copy.copy(args)
+        a.workload, a.scale = w, 1.0
+        try:
+            spec, wname, half = make_spec(a)
+            esz = 2 if half else 8
+            tdt = torch.float16 if half else torch.float64
+            m, n = int(spec.m), int(spec.n)
+            rp, ci, v, nnz = synth.generate(spec, 0, m, dev, half=half)
+            h = dasp_b200.Dasp(dasp_b200.DASP_F16 if half else dasp_b200.DASP_F64, m, n, rp, ci, v, nnz=nnz)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(7)
+            x = (torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdt)
+            y = torch.zeros(m, dtype=tdt, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rows = min(m, 20000)
+            rp_h = rp[: rows + 1].cpu().numpy()
+            k = int(rp_h[-1])
+            f = oracle.csr_spmv_f16 if half else oracle.csr_spmv_f64
+            y_ref = f(rows, rp_h, ci[:k].cpu().numpy(), v[:k].cpu().numpy(), x.cpu().numpy())
+            h.spmv_unpermuted(x, y, stream)
+            torch.cuda.synchronize(dev)
+            err = float(np.linalg.norm(y[:rows].cpu().numpy().astype(np.float64) - y_ref) / max(np.linalg.norm(y_ref), 1e-300))
+            if err > (2e-3 if half else 1e-12):
+                raise RuntimeError(f"parity check failed: {err}")
+            del rp, ci, v
+            torch.cuda.empty_cache()
+            small = algorithmic_bytes(m, n, nnz, esz) < 256e6
+            steps, warm = (2000, 200) if small else (20, 5)
+            ms = h.spmv_timed(x, y, stream, warm, steps) / steps
+            b = algorithmic_bytes(m, n, nnz, esz)
+            out[w] = {"workload": wname, "m": m, "nnz": nnz, "dtype": "f16" if half else "f64", "steps": steps,
+                      "ms_per_step": ms, "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "hbm_gbs": b / (ms * 1e-3) / 1e9,
+                      "hbm_frac_of_8tbs": b / (ms * 1e-3) / 8e12, "parity_check_rel_l2": err,
+                      "l2": "warm L2, back-to-back launches (reference protocol)" if small else "inputs exceed L2"}
+            h.close()
+            del x, y
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[w] = {"error": repr(e)}
+    return out
 
 
 def reference_kernels_leg(args, dev):
