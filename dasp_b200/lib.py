@@ -93,6 +93,10 @@ def load() -> C.CDLL:
         L.dasp_spmv_all_f64.argtypes = [C.c_char_p] + [vp] * 6 + [ip] * 4 + [C.c_double, ip]
         L.dasp_spmv_all_f16.argtypes = [C.c_char_p] + [vp] * 6 + [ip] * 4 + [C.c_double, ip]
         L.dasp_partition_rows.argtypes = [ip, vp, ip, vp]
+        L.dasp_read_mtx.argtypes = [C.c_char_p, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(C.c_int64), C.POINTER(ip),
+                                    C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.dasp_free_host.argtypes = [vp]
+        L.dasp_free_host.restype = None
         L.dasp_sumsq.argtypes = [vp, C.c_int64, vp, vp]
         L.dasp_scale_rsqrt.argtypes = [vp, C.c_int64, vp, vp]
         _lib = L
@@ -238,3 +242,24 @@ def sumsq(d_v, count: int, d_out, stream: int = 0) -> None:
 def scale_rsqrt(d_v, count: int, d_norm2, stream: int = 0) -> None:
     """v *= 1/sqrt(*d_norm2), all on the device."""
     _check(load().dasp_scale_rsqrt(_ptr(d_v), count, _ptr(d_norm2), C.c_void_p(stream)), "dasp_scale_rsqrt")
+
+
+def read_mtx(path: str, dtype: int = DASP_F64):
+    """Matrix Market -> (m, n, rowptr, colidx, val, is_symmetric) with the reference reader's semantics."""
+    L = load()
+    m, n, sym, nnz = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _check(L.dasp_read_mtx(os.fsencode(path), dtype, C.byref(m), C.byref(n), C.byref(nnz), C.byref(sym), C.byref(rp),
+                           C.byref(ci), C.byref(va)), "dasp_read_mtx")
+    try:
+        k = nnz.value
+        rowptr = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int32)), shape=(m.value + 1,)).copy()
+        colidx = np.ctypeslib.as_array(C.cast(ci, C.POINTER(C.c_int32)), shape=(max(k, 1),))[:k].copy()
+        vt = C.c_uint16 if dtype == DASP_F16 else C.c_double
+        val = np.ctypeslib.as_array(C.cast(va, C.POINTER(vt)), shape=(max(k, 1),))[:k].copy()
+        if dtype == DASP_F16:
+            val = val.view(np.float16)
+    finally:
+        for p in (rp, ci, va):
+            L.dasp_free_host(p)
+    return m.value, n.value, rowptr, colidx, val, bool(sym.value)

@@ -151,6 +151,18 @@ int dasp_spmv_all_f16(const char *filename, const void *csrValA, const int *csrR
 int dasp_sumsq(const double *d_v, int64_t count, double *d_out, void *stream);
 int dasp_scale_rsqrt(double *d_v, int64_t count, const double *d_norm2, void *stream);
 
+/* Matrix Market coordinate file -> host CSR, with the reference reader's exact semantics
+ * (mmio_allinone, src/mmio_highlevel.h:608-774) so that a file produces the identical CSR and therefore the
+ * identical DASP layout: 1-based -> 0-based; entries of a row kept in FILE order (columns not sorted, duplicates
+ * kept); `symmetric` and `hermitian` mirrored (off-diagonal entries only, the mirror is appended to its row at the
+ * moment the original is read); `skew-symmetric` NOT expanded; `pattern` -> 1.0; `integer` read as int; `complex`
+ * -> real part.  val is double[nnz] or IEEE-half[nnz] (double rounded to nearest) by dtype.  The three arrays are
+ * malloc'ed; release them with dasp_free_host.  Returns DASP_OK, DASP_ERR_INVALID (cannot open / not a coordinate
+ * Matrix Market file / malformed entry) or DASP_ERR_RANGE (expanded nnz above 2^31-1). */
+int dasp_read_mtx(const char *filename, dasp_dtype dtype, int *m, int *n, int64_t *nnz, int *is_symmetric,
+                  int **rowptr, int **colidx, void **val);
+void dasp_free_host(void *p);
+
 /* nnz-balanced contiguous row partition for multi-GPU runs: cut[p] = smallest i
  * with rowptr[i] >= p*nnz/parts; cuts has parts+1 entries, cut[0]=0, cut[parts]=m. rowptr: host. */
 int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts);

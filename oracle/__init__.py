@@ -212,3 +212,28 @@ def ref_spmv_all(dtype: int, m: int, n: int, rowptr, colidx, val, x=None, thresh
         L.dasp_ref_get(a.encode(), _p(buf), nbytes)
         out[a] = buf.view(dt).copy()
     return out
+
+
+def ref_read_mtx(dtype: int, path: str):
+    """The reference's own mmio_allinone (src/mmio_highlevel.h:608) from oracle/_ref."""
+    L = _ref(dtype)
+    L.dasp_ref_mmio_allinone.restype = C.c_int
+    L.dasp_ref_mmio_allinone.argtypes = [C.c_char_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_void_p)] * 3
+    L.dasp_ref_free.argtypes = [C.c_void_p]
+    L.dasp_ref_free.restype = None
+    m, n, nnz, sym = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    rc = L.dasp_ref_mmio_allinone(os.fsencode(path), C.byref(m), C.byref(n), C.byref(nnz), C.byref(sym), C.byref(rp),
+                                  C.byref(ci), C.byref(va))
+    if rc != 0:
+        return rc, None
+    k = nnz.value
+    rowptr = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int32)), shape=(m.value + 1,)).copy()
+    colidx = np.ctypeslib.as_array(C.cast(ci, C.POINTER(C.c_int32)), shape=(max(k, 1),))[:k].copy()
+    vt = C.c_uint16 if dtype == F16 else C.c_double
+    val = np.ctypeslib.as_array(C.cast(va, C.POINTER(vt)), shape=(max(k, 1),))[:k].copy()
+    if dtype == F16:
+        val = val.view(np.float16)
+    for p in (rp, ci, va):
+        L.dasp_ref_free(p)
+    return 0, (m.value, n.value, rowptr, colidx, val, bool(sym.value))

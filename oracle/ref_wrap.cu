@@ -133,6 +133,13 @@ long dasp_ref_get(const char *name, void *dst, long cap)
     return -1;
 }
 
+/* the reference's Matrix Market reader (src/mmio_highlevel.h:608), for pinning dasp_read_mtx */
+int dasp_ref_mmio_allinone(const char *filename, int *m, int *n, int *nnz, int *is_sym, int **rowptr, int **colidx, void **val)
+{
+    return mmio_allinone(m, n, nnz, is_sym, rowptr, colidx, (MAT_VAL_TYPE **)val, (char *)filename);
+}
+void dasp_ref_free(void *p) { free(p); }
+
 /* the CSV record the reference wrote (structure columns + timing), NUL-terminated */
 const char *dasp_ref_csv(void) { return refhook::g_csv_buf ? refhook::g_csv_buf : ""; }
 
