@@ -212,6 +212,28 @@ int dasp_stats(const dasp_handle *h, dasp_stats_t *out)
     return DASP_OK;
 }
 
+int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *out, int64_t cap)
+{
+    if (!h || !out || cap <= 0 || !(spmv_ms > 0.0)) { set_error("dasp_report: bad argument"); return DASP_ERR_INVALID; }
+    const dasp_stats_t &s = h->L.s;
+    const double gflops = (double)(s.nnz * 2) / (spmv_ms * 1e6);
+    const double bw1 = (double)s.data_X / (spmv_ms * 1e6), bw2 = (double)s.data_X2 / (spmv_ms * 1e6);
+    int k = snprintf(out, (size_t)cap, "%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,", label ? label : "", s.m, s.n,
+                     (int)s.nnz, s.short_row_1, s.common_13, s.short_row_3, s.short_row_4, s.short_row_2, s.row_long,
+                     s.row_block, s.nnz_short, s.fill0_nnz_short, s.nnz_long, s.fill0_nnz_long, s.origin_nnz_reg,
+                     s.fill0_nnz_reg, s.nnz_irreg);
+    if (k < 0 || k >= cap) { set_error("dasp_report: buffer too small"); return DASP_ERR_BUFFER; }
+    int k2;
+    if (h->dtype == DASP_F64)
+        k2 = snprintf(out + k, (size_t)(cap - k), "%lf,%d,%lld,%lf,%lf,%lf,%lf,", s.rate_fill0, h->block_longest,
+                      (long long)s.data_X, spmv_ms, gflops, bw1, bw2);
+    else
+        k2 = snprintf(out + k, (size_t)(cap - k), "%lf,%d,%lld,%lf,%lf,%lf,%lf,%lf,%lf,%lf,", s.rate_fill0, h->block_longest,
+                      (long long)s.data_X, s.preprocess_ms, spmv_ms, gflops, spmv_ms, gflops, bw1, bw2);
+    if (k2 < 0 || k2 >= cap - k) { set_error("dasp_report: buffer too small"); return DASP_ERR_BUFFER; }
+    return k + k2;
+}
+
 int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes, int64_t *bytes)
 {
     if (!h || !name) { set_error("dasp_export: NULL argument"); return DASP_ERR_INVALID; }

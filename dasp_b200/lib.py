@@ -84,6 +84,7 @@ def load() -> C.CDLL:
         L.dasp_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.dasp_export.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.dasp_set_variant.argtypes = [vp, ip, ip, ip]
+        L.dasp_report.argtypes = [vp, C.c_char_p, C.c_double, C.c_char_p, C.c_int64]
         L.dasp_launches_per_spmv.argtypes = [vp]
         L.dasp_set_category_mask.argtypes = [vp, ip]
         L.dasp_destroy.argtypes = [vp]
@@ -183,6 +184,14 @@ class Dasp:
         out = np.empty(nbytes.value // np.dtype(dt).itemsize, dtype=dt)
         _check(load().dasp_export(self._h, name.encode(), _ptr(out), nbytes.value, None), "dasp_export")
         return out
+
+    def report(self, label: str, spmv_ms: float) -> str:
+        """The reference's CSV record (src/dasp_f64.h:1440-1441) for a measured time per SpMV."""
+        buf = C.create_string_buffer(1024)
+        k = load().dasp_report(self._h, label.encode(), spmv_ms, buf, len(buf))
+        if k < 0:
+            _check(k, "dasp_report")
+        return buf.value.decode()
 
     def order_ptr(self) -> int:
         p = C.c_void_p(None)

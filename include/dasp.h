@@ -113,6 +113,15 @@ int dasp_order(const dasp_handle *h, const int **d_order_rid);
 
 int dasp_stats(const dasp_handle *h, dasp_stats_t *out);
 
+/* The reference's reporting surface: the CSV record it appends to data/spmv_f64_record.csv / spmv_f16_record.csv
+ * (src/dasp_f64.h:1440-1441, src/dasp_f16.h:1757-1758), same columns in the same order and printf formats:
+ *   label,rowA,colA,nnzA,short_row_1,common_13,short_row_3,short_row_4,short_row_2,row_long,row_block,nnz_short,
+ *   fill0_nnz_short,nnz_long,fill0_nnz_long,origin_nnz_reg,fill0_nnz_reg,nnz_irreg,rate_fill0,block_longest,data_X,
+ *   [FP16: preprocessing ms,] time ms,GFlop/s,[FP16: time, GFlop/s again (the reference's "bypass" run),]GB/s(data_X),GB/s(data_X2),
+ * for a measured time per SpMV of spmv_ms.  Nothing is written to disk.  Returns the record length (excluding
+ * the NUL) or a negative status; DASP_ERR_BUFFER if cap is too small. */
+int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *out, int64_t cap);
+
 /* Copy one preprocessing output to the host for bit-exact checks.  name is one of:
  * order_rid, long_rpt_new, long_val, long_cid, blockPtr, irreg_rpt, irreg_val, irreg_cid,
  * reg_val, reg_cid, short_val, short_cid.  *bytes receives the array size; host_dst may be NULL

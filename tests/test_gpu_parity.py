@@ -138,3 +138,20 @@ def test_bad_arguments_fail_loudly(dasp, cuda_device):
     with pytest.raises(dasp.DaspError):
         h.export("no_such_array")
     h.close()
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+@pytest.mark.parametrize("name", ["mixed_f1", "powerlaw_20k", "stencil27_12"])
+def test_report_matches_reference_csv_record(dasp, cuda_device, name, dtype):
+    """dasp_report reproduces the structure columns of the record the reference writes (18 structure columns,
+    rate_fill0, block_longest, data_X), compared textually with the reference's own output (oracle/_ref)."""
+    if not oracle.ref_available(dtype):
+        pytest.skip("oracle/_ref not built")
+    m, n, rp, ci, v = get(name)
+    v = v.astype(np.float16 if dtype == oracle.F16 else np.float64)
+    ref = oracle.ref_spmv_all(dtype, m, n, rp, ci, v)["csv"].split(",")
+    h = dasp.Dasp(dtype, m, n, rp, ci, v)
+    got = h.report("ref_wrap", 0.5).split(",")
+    h.close()
+    assert len(got) == len(ref)
+    assert got[:21] == ref[:21], (got[:21], ref[:21])
