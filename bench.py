@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
+    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a"],
+                    help="power iteration: how the y slabs reach every rank (bcast: one NCCL broadcast per slab; a2a: all-to-all "
+                         "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
     return ap.parse_args()
@@ -460,9 +463,23 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     assert m == n, "power iteration needs a square matrix"
     r0, r1 = cuts[rank], cuts[rank + 1]
     stream = torch.cuda.current_stream(dev).cuda_stream
-    xa, xb = x.clone(), torch.zeros_like(x)
+    # The nnz-balanced slabs have very different row counts (C5: the rank holding the short rows owns almost all of
+    # y).  Default exchange: one NCCL broadcast per slab.  Alternative (--exchange a2a): re-cut y into P EQUAL chunks by
+    # global row index, all-to-all the slab pieces to the chunk owners, then all-gather the equal chunks.
+    chunk = (m + world - 1) // world
+    mp = chunk * world
+    xa, xb = torch.zeros(mp, dtype=torch.float64, device=dev), torch.zeros(mp, dtype=torch.float64, device=dev)
+    xa[:m].copy_(x)
     norm2 = torch.zeros(1, dtype=torch.float64, device=dev)
     esz = 8
+    mine = torch.zeros(chunk, dtype=torch.float64, device=dev)
+
+    def overlap(a0, a1, b0, b1):
+        return max(0, min(a1, b1) - max(a0, b0))
+
+    send_split = [overlap(r0, r1, j * chunk, min(m, (j + 1) * chunk)) for j in range(world)]
+    recv_split = [overlap(cuts[p], cuts[p + 1], rank * chunk, min(m, (rank + 1) * chunk)) for p in range(world)]
+    my_len = sum(recv_split)
 
     def step(src, dst):
         h.spmv_unpermuted(src, dst.data_ptr() + r0 * esz, stream)
@@ -470,11 +487,16 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         if world > 1:
             dist.all_reduce(norm2)
         dasp_b200.scale_rsqrt(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
-        if world > 1:
+        if world == 1:
+            return
+        if args.exchange == "bcast":
             works = [dist.broadcast(dst[cuts[p]:cuts[p + 1]], src=p, async_op=True)
                      for p in range(world) if cuts[p + 1] > cuts[p]]
             for w in works:
                 w.wait()
+        else:
+            dist.all_to_all_single(mine[:my_len], dst[r0:r1], output_split_sizes=recv_split, input_split_sizes=send_split)
+            dist.all_gather_into_tensor(dst, mine)
 
     def barrier():
         if world > 1:
@@ -484,7 +506,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     for _ in range(max(3, args.warmup)):
         step(xa, xb)
         xa, xb = xb, xa
-    xa.copy_(x)
+    xa[:m].copy_(x)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -495,7 +517,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     torch.cuda.synchronize(dev)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     lam = float(torch.sqrt(norm2).item())
-    chk = float(xa.double().sum().item())
+    chk = float(xa[:m].sum().item())
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     barrier()
@@ -511,7 +533,9 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wname + f", {args.power_iter}-step power iteration", "m": m, "nnz": nnz_total,
                    "partition": "nnz-balanced contiguous row slabs, x replicated",
-                   "exchange": "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if world > 1 else "none (single GPU)",
+                   "exchange": ("none (single GPU)" if world == 1 else
+                                "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if args.exchange == "bcast" else
+                                "all_reduce(norm^2) + NCCL all_to_all of slab pieces into P equal chunks + all_gather of the chunks"),
                    "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]},
         "spmv_only_ms": float(spmv_ms.item()), "exchange_and_vector_ms": step_ms - float(spmv_ms.item()),
         "eigenvalue_estimate": lam, "x_checksum": chk,
