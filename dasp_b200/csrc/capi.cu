@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "dasp_internal.h"
 
@@ -158,6 +159,115 @@ int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *strea
 {
     if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_unpermuted: NULL argument"); return DASP_ERR_INVALID; }
     return launch_spmv(h, d_x, d_y, h->L.order_rid, (cudaStream_t)stream);
+}
+
+int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, void *d_y, int permuted, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_axpby: NULL argument"); return DASP_ERR_INVALID; }
+    const double ab[2] = {alpha, beta};
+    return launch_spmv(h, d_x, d_y, permuted ? nullptr : h->L.order_rid, (cudaStream_t)stream, ab);
+}
+
+// ---- checkpoint of the preprocessed layout ---------------------------------------------------------
+namespace {
+constexpr uint64_t kMagic = 0x3130305f50534144ull; // "DASP_001"
+struct ArrayRef { void **ptr; int64_t bytes; };
+
+// every device array of the layout with its size, in file order
+int layout_arrays(dasp_handle *h, ArrayRef (&out)[18])
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    const int64_t ev = (int64_t)L.esz, ei = sizeof(int);
+    const int64_t ngroups = ((int64_t)s.row_block + 31) / 32;
+    ArrayRef a[18] = {
+        {(void **)&L.order_rid, ei * s.m},
+        {(void **)&L.long_rpt_new, ei * ((int64_t)s.row_long + 1)},
+        {&L.long_val, ev * s.fill0_nnz_long},
+        {(void **)&L.long_cid, ei * s.fill0_nnz_long},
+        {(void **)&L.blockPtr, ei * ((int64_t)s.blocknum + 1)},
+        {(void **)&L.irreg_rpt, ei * ((int64_t)s.row_block + 1)},
+        {&L.irreg_val, ev * s.fill0_nnz_irreg},
+        {(void **)&L.irreg_cid, ei * s.nnz_irreg},
+        {&L.reg_val, ev * s.fill0_nnz_reg},
+        {(void **)&L.reg_cid, ei * s.fill0_nnz_reg},
+        {&L.short_val, ev * s.fill0_nnz_short},
+        {(void **)&L.short_cid, ei * s.fill0_nnz_short},
+        {(void **)&L.long_unit_row, ei * (int64_t)L.n_long_units},
+        {(void **)&L.long_unit_chunk, ei * (int64_t)L.n_long_units},
+        {(void **)&L.long_unit_first, ei * ((int64_t)s.row_long + 1)},
+        {&L.long_partial, 8 * (int64_t)L.n_long_units},
+        {(void **)&L.long_done, (int64_t)sizeof(unsigned) * s.row_long},
+        {(void **)&L.med_has_irreg, ngroups},
+    };
+    for (int i = 0; i < 18; i++) out[i] = a[i];
+    return 18;
+}
+} // namespace
+
+int dasp_save(const dasp_handle *h, const char *path)
+{
+    if (!h || !path) { set_error("dasp_save: NULL argument"); return DASP_ERR_INVALID; }
+    DASP_CUDA(cudaSetDevice(h->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("dasp_save: cannot open %s", path); return DASP_ERR_INVALID; }
+    ArrayRef arr[18];
+    const int n = layout_arrays(const_cast<dasp_handle *>(h), arr);
+    const int32_t head[4] = {(int32_t)h->dtype, h->block_longest, h->L.n_long_units, n};
+    bool ok = fwrite(&kMagic, 8, 1, f) == 1 && fwrite(head, sizeof(head), 1, f) == 1 && fwrite(&h->threshold, 8, 1, f) == 1 &&
+              fwrite(&h->L.s, sizeof(dasp_stats_t), 1, f) == 1;
+    std::vector<char> buf;
+    for (int i = 0; ok && i < n; i++) {
+        ok = fwrite(&arr[i].bytes, 8, 1, f) == 1;
+        if (!ok || arr[i].bytes == 0) continue;
+        buf.resize((size_t)arr[i].bytes);
+        if (cudaMemcpy(buf.data(), *arr[i].ptr, buf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+        ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error("dasp_save: write to %s failed", path); return DASP_ERR_INVALID; }
+    return DASP_OK;
+}
+
+int dasp_load(dasp_handle **out, const char *path, int device)
+{
+    if (!out || !path) { set_error("dasp_load: NULL argument"); return DASP_ERR_INVALID; }
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("dasp_load: cannot open %s", path); return DASP_ERR_INVALID; }
+    uint64_t magic = 0;
+    int32_t head[4] = {0, 0, 0, 0};
+    double threshold = 0;
+    dasp_stats_t st;
+    bool ok = fread(&magic, 8, 1, f) == 1 && magic == kMagic && fread(head, sizeof(head), 1, f) == 1 &&
+              fread(&threshold, 8, 1, f) == 1 && fread(&st, sizeof(st), 1, f) == 1 && head[3] == 18 &&
+              (head[0] == DASP_F64 || head[0] == DASP_F16);
+    if (!ok) { fclose(f); set_error("dasp_load: %s is not a DASP layout file", path); return DASP_ERR_INVALID; }
+    if (cudaSetDevice(device) != cudaSuccess) { fclose(f); set_error("dasp_load: cudaSetDevice(%d): %s", device, cudaGetErrorString(cudaGetLastError())); return DASP_ERR_CUDA; }
+    dasp_handle *h = new (std::nothrow) dasp_handle();
+    if (!h) { fclose(f); set_error("out of host memory"); return DASP_ERR_ALLOC; }
+    h->device = device; h->dtype = (dasp_dtype)head[0]; h->block_longest = head[1]; h->threshold = threshold;
+    h->L.s = st; h->L.esz = head[0] == DASP_F16 ? 2 : 8; h->L.n_long_units = head[2];
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    int rc = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess ? DASP_OK : DASP_ERR_CUDA;
+    ArrayRef arr[18];
+    const int n = layout_arrays(h, arr);
+    std::vector<char> buf;
+    for (int i = 0; rc == DASP_OK && i < n; i++) {
+        int64_t bytes = -1;
+        if (fread(&bytes, 8, 1, f) != 1 || bytes != arr[i].bytes) { set_error("dasp_load: %s is truncated or inconsistent", path); rc = DASP_ERR_INVALID; break; }
+        if ((rc = h->pool.alloc(arr[i].ptr, (size_t)bytes)) != DASP_OK) break;
+        if (bytes == 0) continue;
+        buf.resize((size_t)bytes);
+        if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { set_error("dasp_load: %s is truncated", path); rc = DASP_ERR_INVALID; break; }
+        if (cudaMemcpy(*arr[i].ptr, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("dasp_load: upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DASP_ERR_CUDA; }
+    }
+    fclose(f);
+    if (rc == DASP_OK && h->L.s.row_long > 0) cudaMemset(h->L.long_done, 0, sizeof(unsigned) * (size_t)h->L.s.row_long);
+    if (rc != DASP_OK) { dasp_destroy(h); return rc; }
+    h->L.s.device_bytes = h->pool.bytes;
+    *out = h;
+    return DASP_OK;
 }
 
 int dasp_spmv_timed(dasp_handle *h, const void *d_x, void *d_y, void *stream, int warmup, int reps, float *total_ms)

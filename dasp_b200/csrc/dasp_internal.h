@@ -92,7 +92,10 @@ namespace dasp {
 int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx,
                const void *d_val, cudaStream_t st);
 // spmv.cu
-int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st);
+int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st,
+                const double *alpha_beta = nullptr);
+int save_layout(const dasp_handle *h, const char *path);
+int load_layout(dasp_handle *h, const char *path);
 int launches_per_spmv(const dasp_handle *h);
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st);
 int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st);

@@ -35,6 +35,8 @@ struct SpmvArgs {
     const void *x;
     void *y;
     const int *scatter; // nullptr: permuted order
+    double alpha, beta; // y = alpha*A*x + beta*y when axpby != 0
+    int axpby;
     // long
     const void *long_val;
     const int *long_cid, *long_rpt_new, *unit_row, *unit_chunk, *unit_first;
@@ -162,8 +164,10 @@ template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(co
 template <typename T>
 __device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Acc<T>::type v)
 {
+    using A = typename Acc<T>::type;
     T *y = static_cast<T *>(a.y);
     if (a.scatter) idx = a.scatter[idx];
+    if (a.axpby) v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * to_acc(y[idx]) : A(0));
     from_acc(y + idx, v);
 }
 
@@ -669,13 +673,16 @@ int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream
     return DASP_OK;
 }
 
-int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st)
+int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st, const double *alpha_beta)
 {
     const Layout &L = h->L;
     const dasp_stats_t &s = L.s;
     const bool f16 = h->dtype == DASP_F16;
     SpmvArgs a{};
     a.x = d_x; a.y = d_y; a.scatter = scatter;
+    a.axpby = alpha_beta ? 1 : 0;
+    a.alpha = alpha_beta ? alpha_beta[0] : 1.0;
+    a.beta = alpha_beta ? alpha_beta[1] : 0.0;
     a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
     a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;

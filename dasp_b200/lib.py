@@ -79,6 +79,9 @@ def load() -> C.CDLL:
         L.dasp_spmv.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_unpermuted.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_host.argtypes = [vp, vp, vp]
+        L.dasp_spmv_axpby.argtypes = [vp, C.c_double, vp, C.c_double, vp, ip, vp]
+        L.dasp_save.argtypes = [vp, C.c_char_p]
+        L.dasp_load.argtypes = [C.POINTER(vp), C.c_char_p, ip]
         L.dasp_spmv_timed.argtypes = [vp, vp, vp, vp, ip, ip, C.POINTER(C.c_float)]
         L.dasp_order.argtypes = [vp, C.POINTER(vp)]
         L.dasp_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -154,6 +157,25 @@ class Dasp:
 
     def spmv_unpermuted(self, d_x, d_y, stream: int = 0) -> None:
         _check(load().dasp_spmv_unpermuted(self._h, _ptr(d_x), _ptr(d_y), C.c_void_p(stream)), "dasp_spmv_unpermuted")
+
+    def spmv_axpby(self, alpha: float, d_x, beta: float, d_y, permuted: bool = True, stream: int = 0) -> None:
+        """y = alpha*A*x + beta*y."""
+        _check(load().dasp_spmv_axpby(self._h, alpha, _ptr(d_x), beta, _ptr(d_y), 1 if permuted else 0, C.c_void_p(stream)),
+               "dasp_spmv_axpby")
+
+    def save(self, path: str) -> None:
+        _check(load().dasp_save(self._h, os.fsencode(path)), "dasp_save")
+
+    @classmethod
+    def load_file(cls, path: str, device: int = 0) -> "Dasp":
+        """Rebuild a handle from a file written by save(): no CSR, no preprocessing."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(None)
+        self._keep = None
+        _check(load().dasp_load(C.byref(self._h), os.fsencode(path), device), "dasp_load")
+        st = self.stats()
+        self.dtype, self.m, self.n, self.nnz = st["dtype"], st["m"], st["n"], st["nnz"]
+        return self
 
     def spmv_timed(self, d_x, d_y, stream: int = 0, warmup: int = 0, reps: int = 1) -> float:
         """`reps` back-to-back launches issued from C; returns their total device time in ms."""

@@ -98,6 +98,16 @@ int dasp_spmv(dasp_handle *h, const void *d_x, void *d_y, void *stream);
  * as the next x (the power-iteration workload). */
 int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *stream);
 
+/* y = alpha*A*x + beta*y (y in permuted order when permuted != 0, original row order otherwise); the general
+ * form solvers need (the reference computes alpha=1, beta=0 only; its cuSPARSE comparator passes alpha/beta,
+ * src/main_f64.cu:23-24).  Rows without entries become beta*y. */
+int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, void *d_y, int permuted, void *stream);
+
+/* Checkpoint of the preprocessed matrix (the layout is a pure function of the CSR): write every array and scalar of
+ * the handle to one binary file / rebuild a handle from it on `device` without the CSR and without preprocessing. */
+int dasp_save(const dasp_handle *h, const char *path);
+int dasp_load(dasp_handle **h, const char *path, int device);
+
 /* Host-buffer convenience with the reference's data movement (src/dasp_f64.h:1241,1402): upload x,
  * run, download y (permuted order), synchronous. */
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host);

@@ -155,3 +155,51 @@ def test_report_matches_reference_csv_record(dasp, cuda_device, name, dtype):
     h.close()
     assert len(got) == len(ref)
     assert got[:21] == ref[:21], (got[:21], ref[:21])
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+def test_axpby_and_checkpoint_roundtrip(dasp, cuda_device, dtype, tmp_path):
+    """y = alpha*A*x + beta*y in both output orders, and a handle rebuilt from its checkpoint file holds the same
+    arrays bit for bit and computes the same y bit for bit."""
+    import torch
+
+    m, n, rp, ci, v = get("mixed_f1")
+    npdt = np.float16 if dtype == oracle.F16 else np.float64
+    tdt = torch.float16 if dtype == oracle.F16 else torch.float64
+    v = v.astype(npdt)
+    x = x_for(n).astype(npdt)
+    y0 = x_for(m, seed=11).astype(npdt)
+    f = oracle.csr_spmv_f16 if dtype == oracle.F16 else oracle.csr_spmv_f64
+    ax = f(m, rp, ci, v, x)
+    h = dasp.Dasp(dtype, m, n, rp, ci, v)
+    order = h.export("order_rid")
+    s = torch.cuda.current_stream().cuda_stream
+    dx = torch.from_numpy(x).to(cuda_device)
+    tol = 1e-12 if dtype == oracle.F64 else 3e-3
+    for alpha, beta in ((1.0, 0.0), (2.5, -0.75), (0.0, 1.0), (-1.0, 0.0)):
+        for permuted in (True, False):
+            dy = torch.from_numpy(y0.copy()).to(cuda_device)
+            h.spmv_axpby(alpha, dx, beta, dy, permuted, s)
+            torch.cuda.synchronize()
+            got = dy.cpu().numpy().astype(np.float64)
+            want = alpha * (ax[order] if permuted else ax) + beta * y0.astype(np.float64)
+            assert np.linalg.norm(got - want) <= tol * max(np.linalg.norm(want), 1.0), (alpha, beta, permuted)
+    path = str(tmp_path / "layout.dasp")
+    h.save(path)
+    h2 = dasp.Dasp.load_file(path)
+    assert (h2.m, h2.n, h2.nnz, h2.dtype) == (m, n, int(rp[m]), dtype)
+    for a in dasp.lib.ARRAYS:
+        assert np.array_equal(h.export(a).view(np.uint8), h2.export(a).view(np.uint8)), a
+    st1, st2 = h.stats(), h2.stats()
+    assert {k: st1[k] for k in st1 if k not in ("device_bytes",)} == {k: st2[k] for k in st2 if k not in ("device_bytes",)}
+    ya = torch.zeros(m, dtype=tdt, device=cuda_device)
+    yb = torch.zeros(m, dtype=tdt, device=cuda_device)
+    for rep in range(2):
+        h.spmv(dx, ya, s)
+        h2.spmv(dx, yb, s)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(ya, yb))
+    h.close()
+    h2.close()
+    with pytest.raises(dasp.DaspError):
+        dasp.Dasp.load_file(str(tmp_path / "missing.dasp"))
