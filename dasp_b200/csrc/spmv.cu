@@ -31,6 +31,7 @@ constexpr int LONG_UNIT_WARPS = 32; // must match preprocess.cu
 constexpr int SINGLES_PER_THREAD = 4;
 constexpr int SHORT_TILES_PER_WARP = 4;
 
+
 struct SpmvArgs {
     const void *x;
     void *y;
@@ -384,32 +385,98 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
     } else {
         const int b = g >> 3, r = g & 7;
         const int bp0 = __ldg(a.blockPtr + b), bp1 = __ldg(a.blockPtr + b + 1);
+        // Bounds of the irregular tail, requested together with the block bounds so that the dependent chain of a
+        // row is {bounds} -> {tiles, tail entries} -> {gathers}.  Large matrices skip the read for the 32-row
+        // groups that have no irregular entry at all (1 flag byte per group instead of 128 bytes of irreg_rpt).
+        int lo = 0, hi = 0;
+        if (g < a.row_block && (KEEP || a.has_irreg[group])) { lo = __ldg(a.irreg_rpt + g); hi = __ldg(a.irreg_rpt + g + 1); }
         const T *pv = val + bp0 + 4 * r;
         const int *pc = a.reg_cid + bp0 + 4 * r;
+        const T *iv = static_cast<const T *>(a.irreg_val);
         const int nt = (bp1 - bp0) >> 5;
-        // four tiles (4 x (256-bit values + 128-bit indices)) in flight per lane; the last batch is predicated
-        for (int k = 0; k < nt; k += 4) {
-            T v[4][4];
-            int c[4][4];
+        if constexpr (!KEEP) {
+            // Large matrices (bandwidth-bound): four tiles (4 x (256-bit values + 128-bit indices)) in flight per
+            // lane, consumed as they arrive (40 registers, 6 CTAs per SM); the last batch is predicated.
+            for (int k = 0; k < nt; k += 4) {
+                T v[4][4];
+                int c[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
-                else {
+                for (int j = 0; j < 4; j++) {
+                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
+                    else {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                        for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                    }
                 }
+                A xv[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
             }
-            A xv[4][4];
+            for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
+        } else {
+            // Small, L2-resident matrices (latency-bound: one launch is a handful of dependent round trips): B
+            // tiles per batch, two batches in flight, software pipelined by hand (the asm loads keep program order) so
+            // the streams of batch i+1 are requested before the gathers of batch i are consumed, and the first
+            // entries of the irregular tail travel with the first batch.  FMA order = CSR order in both paths.
+            // measured on C1/C2 (profiles/r01/README.md): FP64 10.6/10.7/12.1/14.3 us for B = 1/2/3/4, FP16 (blocks are
+            // multiples of 4 tiles) 10.2/9.9/10.2/9.2 us
+            constexpr int B = sizeof(T) == 8 ? 2 : 4;
+            T va[B][4], vb[B][4];
+            int ca[B][4], cb[B][4];
+            auto load = [&](T(&v)[B][4], int(&c)[B][4], int k) {
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+                for (int j = 0; j < B; j++) {
+                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
+                    else {
 #pragma unroll
-                for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+                        for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                    }
+                }
+            };
+            auto consume = [&](const T(&v)[B][4], const int(&c)[B][4]) {
+                A xv[B][4];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+                for (int j = 0; j < B; j++)
 #pragma unroll
-                for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+#pragma unroll
+                for (int j = 0; j < B; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+            };
+            load(va, ca, 0);
+            constexpr int IR = 2;
+            T wv[IR];
+            int wc[IR];
+#pragma unroll
+            for (int j = 0; j < IR; j++) {
+                const bool ok = lo + j < hi;
+                wv[j] = ok ? ld_stream1(iv + lo + j, pol) : T(0);
+                wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
+            }
+            for (int k = 0; k < nt; k += 2 * B) {
+                load(vb, cb, k + B);
+                consume(va, ca);
+                load(va, ca, k + 2 * B);
+                consume(vb, cb);
+            }
+            A xw[IR];
+#pragma unroll
+            for (int j = 0; j < IR; j++) xw[j] = gather(x, wc[j]);
+#pragma unroll
+            for (int j = 0; j < IR; j++) acc += to_acc(wv[j]) * xw[j];
+            for (int i = lo + IR; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
         }
+        if (g < a.row_block) store_y<T>(a, (long)a.row_long + g, acc);
+        return;
     }
+    // DMMA variant: irregular tail and store
     if (g >= a.row_block) return;
     if (a.has_irreg[group]) {
         const T *iv = static_cast<const T *>(a.irreg_val);
