@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
     ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a"],
                     help="power iteration: how the y slabs reach every rank (bcast: one NCCL broadcast per slab; a2a: all-to-all "
@@ -294,6 +295,8 @@ def run_ours(args):
         del rp, ci, v
         torch.cuda.empty_cache()
 
+    if args.categories != 15:
+        h.set_category_mask(args.categories)
     small = algorithmic_bytes(r1 - r0, n, nnz, esz) < 256e6
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev) if (small and args.cold) else None
 
