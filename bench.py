@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--no-index-compression", action="store_true", help="A/B aid: kernels read reg_cid instead of the compact 16-bit indices")
     ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
     ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a"],
@@ -297,6 +298,8 @@ def run_ours(args):
 
     if args.categories != 15:
         h.set_category_mask(args.categories)
+    if args.no_index_compression:
+        h.set_index_compression(False)
     small = algorithmic_bytes(r1 - r0, n, nnz, esz) < 256e6
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev) if (small and args.cold) else None
 

@@ -67,6 +67,11 @@ struct Layout {
     int *long_unit_first = nullptr; // [row_long+1]  first unit of each long row
     void *long_partial = nullptr;   // [n_long_units] double (f64) / float (f16) partial sums
     unsigned *long_done = nullptr;  // [row_long] arrival counters (self-resetting)
+    // compact column indices of the regular part (resident form read by the kernels; reg_cid is kept for export and
+    // for blocks that cannot be compressed): per 8x4 tile one 32-bit base + 32 16-bit offsets, 0xFFFF = column 0
+    int *reg_cbase = nullptr;              // [fill0_nnz_reg / 32]
+    unsigned short *reg_cdelta = nullptr;  // [fill0_nnz_reg]
+    unsigned char *blk_wide = nullptr;     // [blocknum] 1: some tile of the block spans >= 65535 columns -> use reg_cid
     unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
 };
 
@@ -80,7 +85,9 @@ struct dasp_handle {
     dasp::Layout L;
     dasp::DevicePool pool;
     int category_mask = 15;
+    int index_compression = 1;
     int sm_count = 0;
+    const void *carved_kernel = nullptr; // kernel whose L1 carve-out preference was already set on this device
     dasp_variant var_medium = DASP_VARIANT_AUTO, var_long = DASP_VARIANT_AUTO, var_short = DASP_VARIANT_AUTO;
     // device staging of x / y for dasp_spmv_host (owned by pool)
     void *dx_stage = nullptr, *dy_stage = nullptr;

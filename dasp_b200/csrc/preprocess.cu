@@ -334,6 +334,34 @@ __global__ void flag_irreg(const int *__restrict__ irreg_rpt, int row_block, int
     flag[g] = irreg_rpt[hi] != irreg_rpt[32 * g];
 }
 
+// Resident compact form of reg_cid: one warp per 8-row block walks its tiles; per tile the smallest non-zero
+// column is the base and every slot stores (column - base) in 16 bits.  Column 0 (all padding slots, and genuine
+// entries of column 0) is the sentinel 0xFFFF, so the kernels gather exactly the x entries the reference layout
+// names.  A block with a tile spanning >= 65535 columns is flagged wide and keeps using reg_cid.
+__global__ void compress_cid(const int *__restrict__ blockPtr, const int *__restrict__ reg_cid, int blocknum,
+                             int *__restrict__ cbase, unsigned short *__restrict__ cdelta, unsigned char *__restrict__ wide)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= blocknum) return;
+    const int lane = threadIdx.x & 31;
+    const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
+    bool any_wide = false;
+    for (int p = bp0; p < bp1; p += 32) {
+        const int c = reg_cid[p + lane];
+        int mn = c ? c : INT32_MAX, mx = c;
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == INT32_MAX) mn = 0; // tile of zeros only
+        const bool ok = (mx - mn) < 65535;
+        any_wide |= !ok;
+        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
+        if (lane == 0) cbase[p >> 5] = mn;
+    }
+    if (lane == 0) wide[b] = any_wide ? 1 : 0;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -479,6 +507,9 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(pool.alloc((void **)&L.long_done, sizeof(unsigned) * (size_t)cl));
     const int ngroups = ceil_div(cm, 32);
     DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
+    DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
+    DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
+    DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
     DASP_CUDA(cudaMemsetAsync(L.long_val, 0, sizeof(T) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.long_cid, 0, sizeof(int) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.short_val, 0, sizeof(T) * (size_t)s.fill0_nnz_short, st));
@@ -517,6 +548,9 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     if (blocknum > 0)
         pack_reg<T, F16><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(rowptr, colidx, val, ms, ml, L.blockPtr, L.irreg_rpt,
                                                                                cm, blocknum, (T *)L.reg_val, L.reg_cid);
+    if (blocknum > 0)
+        compress_cid<<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(L.blockPtr, L.reg_cid, blocknum, L.reg_cbase,
+                                                                          L.reg_cdelta, L.blk_wide);
     // ---- P10: order_rid ----
     OrderGeom og;
     og.cl = cl; og.cm = cm; og.n1 = n1; og.c13 = c13; og.n3 = n3; og.c4 = c4; og.c2 = c2; og.c0 = c0;

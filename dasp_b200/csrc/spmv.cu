@@ -4,13 +4,16 @@
 // src/dasp_f16.h:106-590).  One fused launch; the block index selects the row category like the
 // reference does (src/dasp_f64.h:90,145,281,296,357,424), but the geometry is this implementation's:
 //
-//   long    one warp per work unit (<= 32 reference warps = 2048/8192 slots of ONE row); 128-bit value
-//           and 64-bit index loads; a row that spans several units is merged deterministically by the
+//   long    one warp per work unit (<= 32 reference warps = 2048/8192 slots of ONE row), 32-slot coalesced
+//           loads, software pipelined; units are enumerated chunk-major over groups of 8 rows so the warps of
+//           a CTA share x sectors in L1; a row that spans several units is merged deterministically by the
 //           last unit to arrive (self-resetting counter) — no second launch (K1+K2 of SURVEY §8a).
+//           Alternatives behind dasp_set_variant: DMMA tiles, TMA bulk-copy ring.
 //   medium  one warp per 4 blocks of 8 rows; lane = (block, row).  CUDA-core variant: every lane walks
 //           the 8x4 tiles of its row with one 256-bit value load + one 128-bit index load per tile and
-//           keeps its own accumulator (no cross-lane traffic, same summation order as serial CSR).
-//           MMA variant: the reference's DMMA m8n8k4 formulation on the same tiles (K3).
+//           keeps its own accumulator (no cross-lane traffic, same summation order as serial CSR); a
+//           latency-oriented pipelined form of the same loop for small, L2-resident matrices (KEEP).
+//           Alternatives: the reference's DMMA m8n8k4 formulation on the same tiles (K3), 4 lanes per row.
 //   short   1 / 1&3 / 3&4 / 2&2 segments read as flat coalesced streams (alignment-free: the FP64
 //           short segments start at slot short_row_1, which is not a multiple of 4) and folded with
 //           shuffles inside each 4-slot tile row (K4-K7).
@@ -19,6 +22,8 @@
 //
 // y is produced in permuted order (K11); with `scatter` (= order_rid) it is written to original order.
 #include <cuda_fp16.h>
+
+#include <type_traits>
 
 #include "dasp_internal.h"
 
@@ -30,7 +35,12 @@ constexpr int WARPS = CTA / 32;
 constexpr int LONG_UNIT_WARPS = 32; // must match preprocess.cu
 constexpr int SINGLES_PER_THREAD = 4;
 constexpr int SHORT_TILES_PER_WARP = 4;
-
+#ifndef MED_TB
+#define MED_TB 4 // tiles per batch of the large-matrix medium kernel (compact-index path)
+#endif
+#ifndef MED_MINB
+#define MED_MINB 6 // CTAs per SM the large-matrix kernels are compiled for
+#endif
 
 struct SpmvArgs {
     const void *x;
@@ -50,6 +60,9 @@ struct SpmvArgs {
     const void *irreg_val;
     const int *irreg_cid;
     const unsigned char *has_irreg;
+    const int *reg_cbase;             // compact indices: per-tile base
+    const unsigned short *reg_cdelta; //                  per-slot 16-bit offset, 0xFFFF = column 0
+    const unsigned char *blk_wide;    // nullptr: compression off; else 1 = block reads reg_cid
     int row_long, row_block, blocknum;
     // short
     const void *short_val;
@@ -105,6 +118,15 @@ template <bool KEEP> __device__ __forceinline__ void ld_stream4(const __half *p,
     asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol.desc));
     __half2 h0 = *reinterpret_cast<__half2 *>(&a), h1 = *reinterpret_cast<__half2 *>(&b);
     v[0] = __low2half(h0); v[1] = __high2half(h0); v[2] = __low2half(h1); v[3] = __high2half(h1);
+}
+// four 16-bit column offsets of one tile row (8 bytes) decoded against the tile base
+__device__ __forceinline__ void ld_stream4_cdelta(const unsigned short *p, int base, int (&c)[4], const StreamPol &pol)
+{
+    unsigned a, b;
+    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol.desc));
+    const unsigned d[4] = {a & 0xFFFFu, a >> 16, b & 0xFFFFu, b >> 16};
+#pragma unroll
+    for (int e = 0; e < 4; e++) c[e] = d[e] == 0xFFFFu ? 0 : base + (int)d[e];
 }
 template <bool KEEP> __device__ __forceinline__ void ld_stream4(const int *p, int (&v)[4], const StreamPol &pol)
 {
@@ -394,29 +416,73 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
         const int *pc = a.reg_cid + bp0 + 4 * r;
         const T *iv = static_cast<const T *>(a.irreg_val);
         const int nt = (bp1 - bp0) >> 5;
+        // column indices of tile k: compact form (tile base + 16-bit offsets) unless a block of this warp is flagged
+        // wide (warp-uniform choice: no divergence, one code path live at a time)
+        const bool compact = __all_sync(0xffffffffu, a.blk_wide != nullptr && a.blk_wide[b] == 0);
+        const unsigned short *pd = a.reg_cdelta + bp0 + 4 * r;
+        const int *pb = a.reg_cbase + (bp0 >> 5);
+        auto load_cid = [&](int k, int(&c)[4]) {
+            if (compact) ld_stream4_cdelta(pd + 32 * k, __ldg(pb + k), c, pol);
+            else ld_stream4<KEEP>(pc + 32 * k, c, pol);
+        };
         if constexpr (!KEEP) {
             // Large matrices (bandwidth-bound): four tiles (4 x (256-bit values + 128-bit indices)) in flight per
             // lane, consumed as they arrive (40 registers, 6 CTAs per SM); the last batch is predicated.
-            for (int k = 0; k < nt; k += 4) {
-                T v[4][4];
-                int c[4][4];
+            if (compact) {
+                // compact indices: 8 bytes of 16-bit offsets + a broadcast 32-bit tile base per tile, decoded just
+                // before the gathers so that only the packed form is live while the loads are in flight
+                for (int k = 0; k < nt; k += MED_TB) {
+                    T v[MED_TB][4];
+                    unsigned d[MED_TB][2];
+                    int base[MED_TB];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
-                    else {
+                    for (int j = 0; j < MED_TB; j++) {
+                        if (k + j < nt) {
+                            ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol);
+                            asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;"
+                                         : "=r"(d[j][0]), "=r"(d[j][1]) : "l"(pd + 32 * (k + j)), "l"(pol.desc));
+                            base[j] = __ldg(pb + k + j);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                            for (int e = 0; e < 4; e++) v[j][e] = T(0);
+                            d[j][0] = d[j][1] = 0xFFFFFFFFu;
+                            base[j] = 0;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < MED_TB; j++) {
+                        A xv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const unsigned h16 = (e & 1) ? (d[j][e >> 1] >> 16) : (d[j][e >> 1] & 0xFFFFu);
+                            xv[e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[e];
                     }
                 }
-                A xv[4][4];
+            } else {
+                for (int k = 0; k < nt; k += 4) {
+                    T v[4][4];
+                    int c[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                    for (int j = 0; j < 4; j++) {
+                        if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
+                        else {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+                            for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                        }
+                    }
+                    A xv[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                    for (int j = 0; j < 4; j++)
 #pragma unroll
-                    for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+                        for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+                }
             }
             for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
         } else {
@@ -432,7 +498,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
             auto load = [&](T(&v)[B][4], int(&c)[B][4], int k) {
 #pragma unroll
                 for (int j = 0; j < B; j++) {
-                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
+                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); load_cid(k + j, c[j]); }
                     else {
 #pragma unroll
                         for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
@@ -663,7 +729,7 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
 
 // One warp per work item; the block index selects the category (grid = sum of the per-category CTA counts).
 template <typename T, int MED, int LONGV, bool KEEP>
-__global__ void __launch_bounds__(CTA, KEEP ? 1 : 6) spmv_kernel(const __grid_constant__ SpmvArgs a)
+__global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
@@ -755,6 +821,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
     a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
     a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
+    a.reg_cbase = L.reg_cbase; a.reg_cdelta = L.reg_cdelta; a.blk_wide = h->index_compression ? L.blk_wide : nullptr;
     a.row_long = s.row_long; a.row_block = s.row_block; a.blocknum = s.blocknum;
     a.short_val = L.short_val; a.short_cid = L.short_cid;
     a.n1 = s.short_row_1; a.c13 = s.common_13; a.n34 = s.short_row_34; a.n2 = s.short_row_2;
@@ -808,10 +875,10 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // reference does (src/dasp_f64.h:1280-1283)
 #define DASP_LAUNCH(T, MED, LV, KEEP)                                                                              \
     do {                                                                                                           \
-        static bool carved = false;                                                                                \
-        if (!carved && LV != 2) {                                                                                  \
+        const void *fn = (const void *)spmv_kernel<T, MED, LV, KEEP>;                                              \
+        if (h->carved_kernel != fn && LV != 2) { /* once per handle (= per device) and kernel */                   \
             cudaFuncSetAttribute(spmv_kernel<T, MED, LV, KEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
-            carved = true;                                                                                         \
+            h->carved_kernel = fn;                                                                                 \
         }                                                                                                          \
         spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                         \
     } while (0)

@@ -90,6 +90,7 @@ def load() -> C.CDLL:
         L.dasp_report.argtypes = [vp, C.c_char_p, C.c_double, C.c_char_p, C.c_int64]
         L.dasp_launches_per_spmv.argtypes = [vp]
         L.dasp_set_category_mask.argtypes = [vp, ip]
+        L.dasp_set_index_compression.argtypes = [vp, ip]
         L.dasp_destroy.argtypes = [vp]
         L.dasp_strerror.restype = C.c_char_p
         L.dasp_strerror.argtypes = [ip]
@@ -222,6 +223,9 @@ class Dasp:
 
     def set_variant(self, medium: int = 0, long_rows: int = 0, short_rows: int = 0) -> None:
         _check(load().dasp_set_variant(self._h, medium, long_rows, short_rows), "dasp_set_variant")
+
+    def set_index_compression(self, on: bool) -> None:
+        _check(load().dasp_set_index_compression(self._h, 1 if on else 0), "dasp_set_index_compression")
 
     def set_category_mask(self, mask: int) -> None:
         """Profiling aid: bit 0 long, 1 medium, 2 short, 3 empty rows."""

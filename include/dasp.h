@@ -141,6 +141,12 @@ int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t 
 
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 
+/* The medium-row kernels read a compact resident copy of the regular part's column indices (per 8x4 tile one
+ * 32-bit base + 16-bit offsets, 10.1 instead of 12 bytes per FP64 slot) and fall back to reg_cid for blocks whose
+ * tiles span >= 65535 columns.  reg_cid itself stays bit-exact and exportable.  on = 0 makes the kernels read
+ * reg_cid everywhere (A/B measurements); default 1. */
+int dasp_set_index_compression(dasp_handle *h, int on);
+
 /* Profiling aid: restrict dasp_spmv to some row categories (bit 0 long, bit 1 medium, bit 2 short,
  * bit 3 empty rows; default 15 = all).  y entries of disabled categories are left untouched. */
 int dasp_set_category_mask(dasp_handle *h, int mask);

@@ -21,6 +21,32 @@ def _pairs(k):
     return _lens(lens, seed=k)
 
 
+def _wide_mixed():
+    """Medium rows whose columns sit in a narrow window (compressible tiles), rows spanning > 65535 columns (wide
+    blocks), rows that contain column 0, and a row with columns exactly 65534 / 65535 / 65536 apart."""
+    rng = np.random.default_rng(33)
+    n = 200000
+    rows = []
+    for i in range(400):
+        L = int(rng.integers(5, 60))
+        if i % 7 == 0:
+            cols = rng.choice(n, L, replace=False)                       # wide
+        elif i % 7 == 1:
+            cols = np.concatenate([[0], 1 + rng.choice(3000, L - 1, replace=False)])  # column 0 + narrow
+        else:
+            lo = int(rng.integers(0, n - 4000))
+            cols = lo + rng.choice(4000, L, replace=False)               # narrow
+        rows.append(cols)
+    for span in (65534, 65535, 65536):
+        rows += [np.array([1000, 1000 + span, 1001, 1002, 1003, 1004, 1005, 1006])] * 8
+    lens = np.array([len(r) for r in rows])
+    rowptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    colidx = np.concatenate(rows).astype(np.int32)
+    val = rng.uniform(-1, 1, len(colidx))
+    return len(rows), n, rowptr.astype(np.int32), colidx, val
+
+
 CASES = {
     # every category populated (fixture F1 of SURVEY.md Appendix A)
     "mixed_f1": lambda: M.mixed(),
@@ -45,6 +71,9 @@ CASES = {
     "one_row_70000": lambda: _lens([70000, 3, 1, 12], n=80000, seed=2),
     "long_pad_64k": lambda: _lens([64, 65, 128, 129, 4096, 4097] * 3 + [300] * 50, n=8192, seed=4),
     "ragged_tail_blocks": lambda: _lens(list(range(5, 90)) + [200, 199, 17] * 11, n=1024, seed=6),
+    # column spans around the 16-bit limit of the compact index form: every tile wide / mixed / column 0 present
+    "wide_span_all": lambda: _lens([40] * 200 + [7] * 30, n=300000, seed=21),
+    "wide_span_mixed": lambda: _wide_mixed(),
     "rowloop_59989": lambda: _lens([5] * 59989 + [1, 2, 3], n=70000, seed=8, window=64),
     "rowloop_59990": lambda: _lens([5] * 59990 + [1, 2, 3], n=70000, seed=8, window=64),
     "rowloop_400000": lambda: _lens([6] * 400000, n=400000, seed=9, window=64),

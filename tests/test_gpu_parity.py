@@ -82,6 +82,14 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
                 else:
                     assert np.max(np.abs(y.astype(np.float64) - y_ref[order]), initial=0.0) <= FP16_ABS_TOL
                     assert _rel_l2(y, y_ref[order]) <= FP16_REL_TOL, f"{name}"
+            # the same product with the kernels reading reg_cid instead of the compact 16-bit indices: bit-equal
+            if variant == dasp.VARIANT_CUDA_CORE:
+                h.set_index_compression(False)
+                dy2 = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
+                h.spmv(dx, dy2, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                h.set_index_compression(True)
+                assert bool(torch.equal(dy2, dy)), f"{name}: compact indices change the result"
             # original-order output
             dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
             h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
