@@ -174,13 +174,13 @@ constexpr uint64_t kMagic = 0x3130305f50534144ull; // "DASP_001"
 struct ArrayRef { void **ptr; int64_t bytes; };
 
 // every device array of the layout with its size, in file order
-int layout_arrays(dasp_handle *h, ArrayRef (&out)[21])
+int layout_arrays(dasp_handle *h, ArrayRef (&out)[24])
 {
     Layout &L = h->L;
     const dasp_stats_t &s = L.s;
     const int64_t ev = (int64_t)L.esz, ei = sizeof(int);
     const int64_t ngroups = ((int64_t)s.row_block + 31) / 32;
-    ArrayRef a[21] = {
+    ArrayRef a[24] = {
         {(void **)&L.order_rid, ei * s.m},
         {(void **)&L.long_rpt_new, ei * ((int64_t)s.row_long + 1)},
         {&L.long_val, ev * s.fill0_nnz_long},
@@ -202,9 +202,12 @@ int layout_arrays(dasp_handle *h, ArrayRef (&out)[21])
         {(void **)&L.reg_cbase, ei * (int64_t)(s.fill0_nnz_reg / 32)},
         {(void **)&L.reg_cdelta, 2 * (int64_t)s.fill0_nnz_reg},
         {(void **)&L.blk_wide, (int64_t)s.blocknum},
+        {(void **)&L.long_cbase, ei * (int64_t)(s.fill0_nnz_long / 32)},
+        {(void **)&L.long_cdelta, 2 * (int64_t)s.fill0_nnz_long},
+        {(void **)&L.long_wide, (int64_t)L.n_long_units},
     };
-    for (int i = 0; i < 21; i++) out[i] = a[i];
-    return 21;
+    for (int i = 0; i < 24; i++) out[i] = a[i];
+    return 24;
 }
 } // namespace
 
@@ -214,7 +217,7 @@ int dasp_save(const dasp_handle *h, const char *path)
     DASP_CUDA(cudaSetDevice(h->device));
     FILE *f = fopen(path, "wb");
     if (!f) { set_error("dasp_save: cannot open %s", path); return DASP_ERR_INVALID; }
-    ArrayRef arr[21];
+    ArrayRef arr[24];
     const int n = layout_arrays(const_cast<dasp_handle *>(h), arr);
     const int32_t head[4] = {(int32_t)h->dtype, h->block_longest, h->L.n_long_units, n};
     bool ok = fwrite(&kMagic, 8, 1, f) == 1 && fwrite(head, sizeof(head), 1, f) == 1 && fwrite(&h->threshold, 8, 1, f) == 1 &&
@@ -243,7 +246,7 @@ int dasp_load(dasp_handle **out, const char *path, int device)
     double threshold = 0;
     dasp_stats_t st;
     bool ok = fread(&magic, 8, 1, f) == 1 && magic == kMagic && fread(head, sizeof(head), 1, f) == 1 &&
-              fread(&threshold, 8, 1, f) == 1 && fread(&st, sizeof(st), 1, f) == 1 && head[3] == 21 &&
+              fread(&threshold, 8, 1, f) == 1 && fread(&st, sizeof(st), 1, f) == 1 && head[3] == 24 &&
               (head[0] == DASP_F64 || head[0] == DASP_F16);
     if (!ok) { fclose(f); set_error("dasp_load: %s is not a DASP layout file", path); return DASP_ERR_INVALID; }
     if (cudaSetDevice(device) != cudaSuccess) { fclose(f); set_error("dasp_load: cudaSetDevice(%d): %s", device, cudaGetErrorString(cudaGetLastError())); return DASP_ERR_CUDA; }
@@ -253,7 +256,7 @@ int dasp_load(dasp_handle **out, const char *path, int device)
     h->L.s = st; h->L.esz = head[0] == DASP_F16 ? 2 : 8; h->L.n_long_units = head[2];
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess ? DASP_OK : DASP_ERR_CUDA;
-    ArrayRef arr[21];
+    ArrayRef arr[24];
     const int n = layout_arrays(h, arr);
     std::vector<char> buf;
     for (int i = 0; rc == DASP_OK && i < n; i++) {

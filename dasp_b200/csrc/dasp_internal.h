@@ -72,6 +72,9 @@ struct Layout {
     int *reg_cbase = nullptr;              // [fill0_nnz_reg / 32]
     unsigned short *reg_cdelta = nullptr;  // [fill0_nnz_reg]
     unsigned char *blk_wide = nullptr;     // [blocknum] 1: some tile of the block spans >= 65535 columns -> use reg_cid
+    int *long_cbase = nullptr;              // [fill0_nnz_long / 32] same compact form for the long part
+    unsigned short *long_cdelta = nullptr;  // [fill0_nnz_long]
+    unsigned char *long_wide = nullptr;     // [n_long_units] in execution order
     unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
 };
 

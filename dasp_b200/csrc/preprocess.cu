@@ -362,6 +362,37 @@ __global__ void compress_cid(const int *__restrict__ blockPtr, const int *__rest
     if (lane == 0) wide[b] = any_wide ? 1 : 0;
 }
 
+// The same compact index form for the long part: one warp per work unit (execution order), one base per 32-slot
+// group; a unit with a group spanning >= 65535 columns is flagged wide and keeps using long_cid.
+__global__ void compress_long_cid(const int *__restrict__ unit_row, const int *__restrict__ unit_chunk,
+                                  const int *__restrict__ long_rpt_new, const int *__restrict__ long_cid, int n_units,
+                                  int longw, int unit_warps, int *__restrict__ cbase, unsigned short *__restrict__ cdelta,
+                                  unsigned char *__restrict__ wide)
+{
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_units) return;
+    const int lane = threadIdx.x & 31;
+    const int row = unit_row[u];
+    const long row_end = (long)long_rpt_new[row + 1] * longw;
+    const long beg = (long)long_rpt_new[row] * longw + (long)unit_chunk[u] * unit_warps * longw;
+    const long end = min(beg + (long)unit_warps * longw, row_end);
+    bool any_wide = false;
+    for (long p = beg; p < end; p += 32) {
+        const int c = long_cid[p + lane];
+        int mn = c ? c : INT32_MAX, mx = c;
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == INT32_MAX) mn = 0;
+        const bool ok = (mx - mn) < 65535;
+        any_wide |= !ok;
+        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
+        if (lane == 0) cbase[p >> 5] = mn;
+    }
+    if (lane == 0) wide[u] = any_wide ? 1 : 0;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -507,6 +538,9 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(pool.alloc((void **)&L.long_done, sizeof(unsigned) * (size_t)cl));
     const int ngroups = ceil_div(cm, 32);
     DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
+    DASP_TRY(pool.alloc((void **)&L.long_cbase, sizeof(int) * (size_t)(s.fill0_nnz_long / 32)));
+    DASP_TRY(pool.alloc((void **)&L.long_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_long));
+    DASP_TRY(pool.alloc((void **)&L.long_wide, (size_t)L.n_long_units));
     DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
     DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
     DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
@@ -538,6 +572,9 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         pack_long<T><<<dim3(cl, per_row), 256, 0, st>>>(rowptr, colidx, val, cat_rid + seg[CAT_LONG], L.long_rpt_new, LONGW,
                                                         (T *)L.long_val, L.long_cid);
         fill_long_units<<<(cl + 7) / 8, 128, 0, st>>>(L.long_unit_first, cl, L.long_unit_row, L.long_unit_chunk);
+        compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.long_cid,
+                                                                                   L.n_long_units, LONGW, LONG_UNIT_WARPS, L.long_cbase,
+                                                                                   L.long_cdelta, L.long_wide);
     }
     // ---- P13/P14: medium rows ----
     if (cm > 0) {

@@ -51,6 +51,9 @@ struct SpmvArgs {
     // long
     const void *long_val;
     const int *long_cid, *long_rpt_new, *unit_row, *unit_chunk, *unit_first;
+    const int *long_cbase;             // compact indices of the long part: base per 32-slot group
+    const unsigned short *long_cdelta; //   16-bit offsets, 0xFFFF = column 0
+    const unsigned char *long_wide;    //   per unit (execution order): 1 = read long_cid; nullptr = compression off
     void *partial;
     unsigned *done;
     int n_units, longw;
@@ -144,6 +147,12 @@ __device__ __forceinline__ __half ld_stream1(const __half *p, const StreamPol &p
     unsigned short v;
     asm volatile(DASP_LD_HINT ".u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol.desc));
     return __ushort_as_half(v);
+}
+__device__ __forceinline__ int ld_stream1(const unsigned short *p, const StreamPol &pol)
+{
+    unsigned short v;
+    asm volatile(DASP_LD_HINT ".u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol.desc));
+    return (int)v;
 }
 __device__ __forceinline__ int ld_stream1(const int *p, const StreamPol &pol)
 {
@@ -308,31 +317,47 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
         // predicated off.
         constexpr int LB = 4; // slots per lane per batch = 128 slots per warp
         A s0 = 0, s1 = 0;
-        T v0[LB], v1[LB];
-        int c0[LB], c1[LB];
-        auto load = [&](T(&v)[LB], int(&c)[LB], long q) {
+        // column indices: compact form (one 32-bit base per 32-slot group + 16-bit offsets, decoded only when the
+        // gathers are issued so that nothing depends on a load while the next loads are being requested) unless
+        // this unit holds a group spanning >= 65535 columns
+        auto run = [&](auto tag) {
+            constexpr bool CP = decltype(tag)::value;
+            T v0[LB], v1[LB];
+            int c0[LB], c1[LB], b0[LB], b1[LB];
+            auto load = [&](T(&v)[LB], int(&c)[LB], int(&bs)[LB], long q) {
 #pragma unroll
-            for (int j = 0; j < LB; j++) {
-                const bool ok = q + 32 * j < end;
-                v[j] = ok ? ld_stream1(val + q + 32 * j, pol) : T(0);
-                c[j] = ok ? ld_stream1(a.long_cid + q + 32 * j, pol) : 0;
+                for (int j = 0; j < LB; j++) {
+                    const bool ok = q + 32 * j < end;
+                    v[j] = ok ? ld_stream1(val + q + 32 * j, pol) : T(0);
+                    if constexpr (CP) {
+                        c[j] = ok ? ld_stream1(a.long_cdelta + q + 32 * j, pol) : 0xFFFF;
+                        bs[j] = ok ? __ldg(a.long_cbase + ((q + 32 * j) >> 5)) : 0;
+                    } else {
+                        c[j] = ok ? ld_stream1(a.long_cid + q + 32 * j, pol) : 0;
+                    }
+                }
+            };
+            auto consume = [&](const T(&v)[LB], const int(&c)[LB], const int(&bs)[LB]) {
+                A g[LB];
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    if constexpr (CP) g[j] = gather(x, c[j] == 0xFFFF ? 0 : bs[j] + c[j]);
+                    else g[j] = gather(x, c[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < LB; j += 2) { s0 += to_acc(v[j]) * g[j]; s1 += to_acc(v[j + 1]) * g[j + 1]; }
+            };
+            long p = beg + lane;
+            load(v0, c0, b0, p);
+            for (; p < end; p += 64 * LB) {
+                load(v1, c1, b1, p + 32 * LB);
+                consume(v0, c0, b0);
+                load(v0, c0, b0, p + 64 * LB);
+                consume(v1, c1, b1);
             }
         };
-        auto consume = [&](const T(&v)[LB], const int(&c)[LB]) {
-            A g[LB];
-#pragma unroll
-            for (int j = 0; j < LB; j++) g[j] = gather(x, c[j]);
-#pragma unroll
-            for (int j = 0; j < LB; j += 2) { s0 += to_acc(v[j]) * g[j]; s1 += to_acc(v[j + 1]) * g[j + 1]; }
-        };
-        long p = beg + lane;
-        load(v0, c0, p);
-        for (; p < end; p += 64 * LB) {
-            load(v1, c1, p + 32 * LB);
-            consume(v0, c0);
-            load(v0, c0, p + 64 * LB);
-            consume(v1, c1);
-        }
+        if (a.long_wide != nullptr && __ldg(a.long_wide + u) == 0) run(std::true_type{});
+        else run(std::false_type{});
         acc = warp_sum(s0 + s1);
     }
     if (nunits == 1) {
@@ -449,17 +474,18 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
                             base[j] = 0;
                         }
                     }
+                    A xv[MED_TB][4];
 #pragma unroll
-                    for (int j = 0; j < MED_TB; j++) {
-                        A xv[4];
+                    for (int j = 0; j < MED_TB; j++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const unsigned h16 = (e & 1) ? (d[j][e >> 1] >> 16) : (d[j][e >> 1] & 0xFFFFu);
-                            xv[e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16);
+                            xv[j][e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16);
                         }
 #pragma unroll
-                        for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[e];
-                    }
+                    for (int j = 0; j < MED_TB; j++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
                 }
             } else {
                 for (int k = 0; k < nt; k += 4) {
@@ -819,6 +845,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
     a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
+    a.long_cbase = L.long_cbase; a.long_cdelta = L.long_cdelta; a.long_wide = h->index_compression ? L.long_wide : nullptr;
     a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
     a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
     a.reg_cbase = L.reg_cbase; a.reg_cdelta = L.reg_cdelta; a.blk_wide = h->index_compression ? L.blk_wide : nullptr;
