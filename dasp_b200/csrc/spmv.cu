@@ -122,15 +122,6 @@ template <bool KEEP> __device__ __forceinline__ void ld_stream4(const __half *p,
     __half2 h0 = *reinterpret_cast<__half2 *>(&a), h1 = *reinterpret_cast<__half2 *>(&b);
     v[0] = __low2half(h0); v[1] = __high2half(h0); v[2] = __low2half(h1); v[3] = __high2half(h1);
 }
-// four 16-bit column offsets of one tile row (8 bytes) decoded against the tile base
-__device__ __forceinline__ void ld_stream4_cdelta(const unsigned short *p, int base, int (&c)[4], const StreamPol &pol)
-{
-    unsigned a, b;
-    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(a), "=r"(b) : "l"(p), "l"(pol.desc));
-    const unsigned d[4] = {a & 0xFFFFu, a >> 16, b & 0xFFFFu, b >> 16};
-#pragma unroll
-    for (int e = 0; e < 4; e++) c[e] = d[e] == 0xFFFFu ? 0 : base + (int)d[e];
-}
 template <bool KEEP> __device__ __forceinline__ void ld_stream4(const int *p, int (&v)[4], const StreamPol &pol)
 {
     asm volatile(DASP_LD_HINT ".v4.s32 {%0,%1,%2,%3}, [%4], %5;"
@@ -446,10 +437,6 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
         const bool compact = __all_sync(0xffffffffu, a.blk_wide != nullptr && a.blk_wide[b] == 0);
         const unsigned short *pd = a.reg_cdelta + bp0 + 4 * r;
         const int *pb = a.reg_cbase + (bp0 >> 5);
-        auto load_cid = [&](int k, int(&c)[4]) {
-            if (compact) ld_stream4_cdelta(pd + 32 * k, __ldg(pb + k), c, pol);
-            else ld_stream4<KEEP>(pc + 32 * k, c, pol);
-        };
         if constexpr (!KEEP) {
             // Large matrices (bandwidth-bound): four tiles (4 x (256-bit values + 128-bit indices)) in flight per
             // lane, consumed as they arrive (40 registers, 6 CTAs per SM); the last batch is predicated.
@@ -524,7 +511,8 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
             auto load = [&](T(&v)[B][4], int(&c)[B][4], int k) {
 #pragma unroll
                 for (int j = 0; j < B; j++) {
-                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); load_cid(k + j, c[j]); }
+                    // (latency-bound: the 32-bit reg_cid is read directly, the compact form only pays off when DRAM-bound)
+                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
                     else {
 #pragma unroll
                         for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
