@@ -211,3 +211,28 @@ def test_axpby_and_checkpoint_roundtrip(dasp, cuda_device, dtype, tmp_path):
     h2.close()
     with pytest.raises(dasp.DaspError):
         dasp.Dasp.load_file(str(tmp_path / "missing.dasp"))
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+@pytest.mark.parametrize("threshold,block_longest", [(0.5, 256), (1.0, 256), (0.75, 64), (0.3, 1000), (0.9, 17)])
+def test_non_default_threshold_and_block_longest(dasp, cuda_device, threshold, block_longest, dtype):
+    """The reference's two run-time constants away from 0.75 / 256: layout bit-exact vs the oracle, y correct."""
+    import torch
+
+    for name in ("mixed_f1", "powerlaw_20k"):
+        m, n, rp, ci, v = get(name)
+        npdt = np.float16 if dtype == oracle.F16 else np.float64
+        v = v.astype(npdt)
+        ref = oracle.preprocess(dtype, m, n, rp, ci, v, threshold, block_longest)
+        h = dasp.Dasp(dtype, m, n, rp, ci, v, threshold=threshold, block_longest=block_longest)
+        for a in dasp.lib.ARRAYS:
+            assert np.array_equal(h.export(a).view(np.uint8), ref[a].view(np.uint8)), f"{name}: {a}"
+        x = x_for(n).astype(npdt)
+        dx = torch.from_numpy(x).to(cuda_device)
+        dy = torch.zeros(m, dtype=dx.dtype, device=cuda_device)
+        h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        f = oracle.csr_spmv_f16 if dtype == oracle.F16 else oracle.csr_spmv_f64
+        y_ref = f(m, rp, ci, v, x)
+        assert _rel_l2(dy.cpu().numpy(), y_ref) <= (FP64_TOL if dtype == oracle.F64 else FP16_REL_TOL)
+        h.close()

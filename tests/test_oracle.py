@@ -183,3 +183,18 @@ def test_serial_csr_definition_and_threads_agree():
         assert y[i] == s
     y_mt = oracle.csr_spmv_f64(m, rp, ci, v, x, threads=4)
     assert np.array_equal(y, y_mt)
+
+
+@pytest.mark.skipif(not (oracle.ref_available(oracle.F64) and oracle.ref_available(oracle.F16)),
+                    reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+@pytest.mark.parametrize("threshold,block_longest", [(0.5, 256), (1.0, 256), (0.75, 64), (0.3, 1000), (0.9, 17)])
+def test_oracle_matches_compiled_reference_with_other_parameters(threshold, block_longest, dtype):
+    """The two run-time constants of the reference (src/main_f64.cu:124-125) away from their defaults."""
+    for name in ("mixed_f1", "powerlaw_20k", "ragged_tail_blocks"):
+        m, n, rp, ci, v = get(name)
+        vv = _val(v, dtype)
+        o = _defined(oracle.preprocess(dtype, m, n, rp, ci, vv, threshold, block_longest))
+        r = _defined(oracle.ref_spmv_all(dtype, m, n, rp, ci, vv, threshold=threshold, block_longest=block_longest))
+        for a in ARRAYS:
+            assert np.array_equal(o[a].view(np.uint8), r[a].view(np.uint8)), f"{name}: {a}"
