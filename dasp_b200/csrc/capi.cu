@@ -145,6 +145,11 @@ int dasp_destroy(dasp_handle *h)
     cudaSetDevice(h->device);
     h->pool.free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int k = 0; k < 3; k++) {
+        if (h->batch_stream[k]) cudaStreamDestroy(h->batch_stream[k]);
+        for (int b = 0; b < 2; b++)
+            if (h->batch_ev[k][b]) cudaEventDestroy(h->batch_ev[k][b]);
+    }
     delete h;
     return DASP_OK;
 }
@@ -311,6 +316,45 @@ int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host)
     DASP_TRY(launch_spmv(h, h->dx_stage, h->dy_stage, nullptr, st));
     DASP_CUDA(cudaMemcpyAsync(y_host, h->dy_stage, yb, cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaStreamSynchronize(st));
+    return DASP_OK;
+}
+
+int dasp_spmv_host_batch(dasp_handle *h, const void *const *x_hosts, void *const *y_hosts, int count)
+{
+    if (!h || count < 0 || (count > 0 && (!x_hosts || !y_hosts))) { set_error("dasp_spmv_host_batch: bad argument"); return DASP_ERR_INVALID; }
+    if (count == 0) return DASP_OK;
+    DASP_CUDA(cudaSetDevice(h->device));
+    const size_t esz = h->dtype == DASP_F16 ? 2 : 8;
+    const size_t xb = esz * (size_t)h->L.s.n, yb = esz * (size_t)h->L.s.m;
+    if (!h->batch_stream[0]) {
+        for (int k = 0; k < 3; k++) DASP_CUDA(cudaStreamCreateWithFlags(&h->batch_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; k++)
+            for (int b = 0; b < 2; b++) DASP_CUDA(cudaEventCreateWithFlags(&h->batch_ev[k][b], cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) {
+            DASP_TRY(h->pool.alloc(&h->batch_dx[b], xb));
+            DASP_TRY(h->pool.alloc(&h->batch_dy[b], yb));
+        }
+    }
+    cudaStream_t up = h->batch_stream[0], comp = h->batch_stream[1], down = h->batch_stream[2];
+    cudaEvent_t(&ev)[3][2] = h->batch_ev; // [0] upload done, [1] kernel done, [2] download done, per staging buffer
+    for (int i = 0; i < count; i++) {
+        const int b = i & 1;
+        if (!x_hosts[i] && xb) { set_error("dasp_spmv_host_batch: x_hosts[%d] is NULL", i); return DASP_ERR_INVALID; }
+        if (!y_hosts[i] && yb) { set_error("dasp_spmv_host_batch: y_hosts[%d] is NULL", i); return DASP_ERR_INVALID; }
+        if (i >= 2) DASP_CUDA(cudaStreamWaitEvent(up, ev[1][b], 0)); // x staging b free once product i-2 was multiplied
+        DASP_CUDA(cudaMemcpyAsync(h->batch_dx[b], x_hosts[i], xb, cudaMemcpyHostToDevice, up));
+        DASP_CUDA(cudaEventRecord(ev[0][b], up));
+        DASP_CUDA(cudaStreamWaitEvent(comp, ev[0][b], 0));
+        if (i >= 2) DASP_CUDA(cudaStreamWaitEvent(comp, ev[2][b], 0)); // y staging b free once product i-2 was downloaded
+        DASP_TRY(launch_spmv(h, h->batch_dx[b], h->batch_dy[b], nullptr, comp));
+        DASP_CUDA(cudaEventRecord(ev[1][b], comp));
+        DASP_CUDA(cudaStreamWaitEvent(down, ev[1][b], 0));
+        DASP_CUDA(cudaMemcpyAsync(y_hosts[i], h->batch_dy[b], yb, cudaMemcpyDeviceToHost, down));
+        DASP_CUDA(cudaEventRecord(ev[2][b], down));
+    }
+    DASP_CUDA(cudaStreamSynchronize(down));
+    DASP_CUDA(cudaStreamSynchronize(up));
+    DASP_CUDA(cudaStreamSynchronize(comp));
     return DASP_OK;
 }
 

@@ -95,6 +95,10 @@ struct dasp_handle {
     // device staging of x / y for dasp_spmv_host (owned by pool)
     void *dx_stage = nullptr, *dy_stage = nullptr;
     cudaStream_t own_stream = nullptr;
+    // dasp_spmv_host_batch: upload / compute / download streams, double-buffered staging and hand-over events
+    cudaStream_t batch_stream[3] = {nullptr, nullptr, nullptr};
+    void *batch_dx[2] = {nullptr, nullptr}, *batch_dy[2] = {nullptr, nullptr};
+    cudaEvent_t batch_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 namespace dasp {

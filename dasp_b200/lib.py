@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         L.dasp_spmv.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_unpermuted.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_host.argtypes = [vp, vp, vp]
+        L.dasp_spmv_host_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
         L.dasp_spmv_axpby.argtypes = [vp, C.c_double, vp, C.c_double, vp, ip, vp]
         L.dasp_save.argtypes = [vp, C.c_char_p]
         L.dasp_load.argtypes = [C.POINTER(vp), C.c_char_p, ip]
@@ -193,6 +194,14 @@ class Dasp:
             y_host = np.empty(self.m, dtype=_np_val(self.dtype))
         _check(load().dasp_spmv_host(self._h, _ptr(x_host), _ptr(y_host)), "dasp_spmv_host")
         return y_host
+
+    def spmv_host_batch(self, x_hosts, y_hosts) -> None:
+        """Independent products y_j = A x_j on (preferably pinned) host buffers, copies and kernels pipelined."""
+        k = len(x_hosts)
+        assert len(y_hosts) == k
+        xs = (C.c_void_p * k)(*[_ptr(x) for x in x_hosts])
+        ys = (C.c_void_p * k)(*[_ptr(y) for y in y_hosts])
+        _check(load().dasp_spmv_host_batch(self._h, xs, ys, k), "dasp_spmv_host_batch")
 
     # -- inspect ---------------------------------------------------------------------------------
     def stats(self) -> dict:

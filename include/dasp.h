@@ -112,6 +112,13 @@ int dasp_load(dasp_handle **h, const char *path, int device);
  * run, download y (permuted order), synchronous. */
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host);
 
+/* Host buffers, `count` independent products y_j = A*x_j (several right-hand sides, or a stream of requests):
+ * product j uploads x_hosts[j], multiplies, downloads into y_hosts[j] (permuted order) exactly like dasp_spmv_host,
+ * but the three phases run on three streams with double-buffered device staging, so the upload of product j+1 and
+ * the download of product j-1 overlap the kernel of product j (both PCIe directions busy).  Host buffers should be
+ * pinned (cudaHostAlloc / cudaHostRegister) for the copies to overlap.  Synchronous: returns when all y are in place. */
+int dasp_spmv_host_batch(dasp_handle *h, const void *const *x_hosts, void *const *y_hosts, int count);
+
 /* The reference's measurement loop (src/dasp_f64.h:1285-1320: warm-up launches, then `reps` launches
  * back to back) issued from C so that small matrices are not bound by the caller's launch rate, timed
  * with CUDA events on `stream`.  *total_ms receives the device time of the `reps` launches. */

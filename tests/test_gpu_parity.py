@@ -236,3 +236,24 @@ def test_non_default_threshold_and_block_longest(dasp, cuda_device, threshold, b
         y_ref = f(m, rp, ci, v, x)
         assert _rel_l2(dy.cpu().numpy(), y_ref) <= (FP64_TOL if dtype == oracle.F64 else FP16_REL_TOL)
         h.close()
+
+
+@pytest.mark.parametrize("dtype", [oracle.F64, oracle.F16], ids=["f64", "f16"])
+def test_host_batch_equals_individual_products(dasp, cuda_device, dtype):
+    """dasp_spmv_host_batch (pipelined copies/kernels, double-buffered staging) returns, for every right-hand side,
+    exactly what dasp_spmv_host returns, for batches shorter and longer than the pipeline depth."""
+    import torch
+
+    m, n, rp, ci, v = get("powerlaw_20k")
+    tdt = torch.float16 if dtype == oracle.F16 else torch.float64
+    h = dasp.Dasp(dtype, m, n, rp, ci, v.astype(np.float16 if dtype == oracle.F16 else np.float64))
+    for count in (1, 2, 5):
+        xs = [torch.from_numpy(x_for(n, seed=100 + j)).to(tdt).pin_memory() for j in range(count)]
+        ys = [torch.full((m,), float("nan"), dtype=tdt).pin_memory() for _ in range(count)]
+        h.spmv_host_batch(xs, ys)
+        for j in range(count):
+            want = torch.empty(m, dtype=tdt)
+            h.spmv_host(xs[j], want)
+            assert bool(torch.equal(ys[j], want)), (count, j)
+    h.spmv_host_batch([], [])
+    h.close()
