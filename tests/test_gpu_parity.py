@@ -257,3 +257,28 @@ def test_host_batch_equals_individual_products(dasp, cuda_device, dtype):
             assert bool(torch.equal(ys[j], want)), (count, j)
     h.spmv_host_batch([], [])
     h.close()
+
+
+def test_spmv_is_cuda_graph_capturable(dasp, cuda_device):
+    """dasp_spmv only enqueues one kernel on the caller's stream, so a solver can capture its iteration in a CUDA
+    graph (launch-bound small matrices); replaying the graph gives the same y as direct launches."""
+    import torch
+
+    m, n, rp, ci, v = get("mixed_f1")
+    h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)
+    dx = torch.from_numpy(x_for(n)).to(cuda_device)
+    y_direct = torch.zeros(m, dtype=torch.float64, device=cuda_device)
+    y_graph = torch.zeros(m, dtype=torch.float64, device=cuda_device)
+    h.spmv(dx, y_direct, torch.cuda.current_stream().cuda_stream)  # also sets the kernel attributes before capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(3):
+                h.spmv(dx, y_graph, torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert bool(torch.equal(y_graph, y_direct))
+    h.close()
