@@ -181,6 +181,12 @@ constexpr int TMA_STAGE_BYTES = TMA_STAGE_SLOTS * 12;
 constexpr int TMA_WARP_BYTES = TMA_STAGES * TMA_STAGE_BYTES;
 constexpr int TMA_SMEM_BYTES = WARPS * TMA_WARP_BYTES + WARPS * TMA_STAGES * 8;
 
+// Programmatic dependent launch (small matrices): a KEEP kernel may start while its predecessor on the stream is
+// still draining.  Everything read before pdl_wait() is immutable matrix data; x (possibly the predecessor's y) and y
+// are only touched after it.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // x gathers: read-only path, allocate in L1 (neighbouring rows reuse the same entries)
 template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c) { return to_acc(__ldg(x + c)); }
 
@@ -540,6 +546,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
                 wv[j] = ok ? ld_stream1(iv + lo + j, pol) : T(0);
                 wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
             }
+            pdl_wait(); // streams of the first batch are in flight; x and y may belong to the previous kernel
             for (int k = 0; k < nt; k += 2 * B) {
                 load(vb, cb, k + B);
                 consume(va, ca);
@@ -746,12 +753,15 @@ template <typename T, int MED, int LONGV, bool KEEP>
 __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
+    if constexpr (KEEP) pdl_launch_dependents();
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
     int cat = 0, first = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++)
         if (bid >= a.e[k]) { cat = k + 1; first = a.e[k]; }
     const int local = bid - first;
+    // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
+    if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
     run_category<T, MED, LONGV, KEEP>(a, cat, (long)local * WARPS + warp, dyn_smem);
 }
 
@@ -895,7 +905,16 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
             cudaFuncSetAttribute(spmv_kernel<T, MED, LV, KEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
             h->carved_kernel = fn;                                                                                 \
         }                                                                                                          \
-        spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                         \
+        if (KEEP) { /* small matrices: programmatic dependent launch hides the launch gap between products */     \
+            cudaLaunchConfig_t cfg = {};                                                                            \
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;          \
+            cudaLaunchAttribute at[1];                                                                              \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                                       \
+            DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<T, MED, LV, KEEP>, a));                                  \
+        } else                                                                                                     \
+            spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                     \
     } while (0)
     if (f16) {
         if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
