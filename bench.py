@@ -50,9 +50,11 @@ def parse():
     ap.add_argument("--no-index-compression", action="store_true", help="A/B aid: kernels read reg_cid instead of the compact 16-bit indices")
     ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
-    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a"],
+    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a", "p2p", "mc", "mcu", "p2pu"],
                     help="power iteration: how the y slabs reach every rank (bcast: one NCCL broadcast per slab; a2a: all-to-all "
-                         "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs)")
+                         "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs; p2p / mc: fused, the "
+                         "SpMV kernel stores y straight into every peer's next x through NVLink peer mappings / one NVSwitch "
+                         "multicast mapping, the all-reduce of the norm is the only collective)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
     return ap.parse_args()
@@ -499,22 +501,71 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     recv_split = [overlap(cuts[p], cuts[p + 1], rank * chunk, min(m, (rank + 1) * chunk)) for p in range(world)]
     my_len = sum(recv_split)
 
-    def step(src, dst):
-        h.spmv_unpermuted(src, dst.data_ptr() + r0 * esz, stream)
-        dasp_b200.sumsq(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
-        if world > 1:
-            dist.all_reduce(norm2)
-        dasp_b200.scale_rsqrt(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
-        if world == 1:
-            return
-        if args.exchange == "bcast":
-            works = [dist.broadcast(dst[cuts[p]:cuts[p + 1]], src=p, async_op=True)
-                     for p in range(world) if cuts[p + 1] > cuts[p]]
-            for w in works:
-                w.wait()
-        else:
-            dist.all_to_all_single(mine[:my_len], dst[r0:r1], output_split_sizes=recv_split, input_split_sizes=send_split)
-            dist.all_gather_into_tensor(dst, mine)
+    fused = args.exchange in ("p2p", "mc", "mcu", "p2pu") and world > 1
+    if fused:
+        # Fused product + exchange: both iterates live in symmetric memory; every rank's kernel stores its slab of y
+        # into ALL copies of the next iterate (peer mappings or one multicast mapping).  The vector is kept
+        # un-normalised; the next product scales by 1/sqrt(norm^2), read from device memory, so the only collective
+        # per step is the all-reduce of the squared norm, which is also the barrier that orders the peer stores.
+        import torch.distributed._symmetric_memory as symm
+
+        sbuf = symm.empty(2 * mp, dtype=torch.float64, device=dev)
+        hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+        sbuf.zero_()
+        xa, xb = sbuf[:mp], sbuf[mp:]
+        xa[:m].copy_(x)
+        hdl.barrier()
+        peer = [int(p) for p in hdl.buffer_ptrs]
+        use_mc = args.exchange in ("mc", "mcu")
+        two_pass = args.exchange in ("mcu", "p2pu")
+        yp = torch.zeros(max(r1 - r0, 1), dtype=torch.float64, device=dev) if two_pass else None
+        token = torch.zeros(1, dtype=torch.float32, device=dev)
+        mc_ptr = int(hdl.multicast_ptr) if use_mc else 0
+        if use_mc and mc_ptr == 0:
+            raise SystemExit("bench.py: --exchange mc: no multicast support on this system")
+        nrm = [torch.ones(1, dtype=torch.float64, device=dev), torch.ones(1, dtype=torch.float64, device=dev)]
+        fstate = {"k": 0}
+
+        def dests_of(buf):
+            off = (buf.data_ptr() - sbuf.data_ptr())
+            if use_mc:
+                return [mc_ptr + off]
+            # own copy first, then the peers'
+            return [peer[rank] + off] + [peer[p] + off for p in range(world) if p != rank]
+
+        def step(src, dst):
+            k = fstate["k"]
+            if two_pass:
+                # permuted (coalesced) product, norm, then ONE coalesced un-permute + scale + store-to-all pass
+                h.spmv(src, yp, stream)
+                dasp_b200.sumsq(yp, r1 - r0, norm2, stream)
+                dist.all_reduce(norm2)
+                h.unpermute_to(yp, dests_of(dst), r0, norm2, stream)
+                dist.all_reduce(token)  # orders every rank's stores into this rank's copy before the next product reads it
+                return
+            # y_k = A x_k / ||y_{k-1}||  (x_k is stored un-normalised); the first step scales by 1
+            h.spmv_scatter_to(src, dests_of(dst), r0, nrm[k & 1], stream)
+            dasp_b200.sumsq(dst.data_ptr() + r0 * esz, r1 - r0, nrm[(k + 1) & 1], stream)
+            dist.all_reduce(nrm[(k + 1) & 1])
+            norm2.copy_(nrm[(k + 1) & 1])
+            fstate["k"] = k + 1
+    else:
+        def step(src, dst):
+            h.spmv_unpermuted(src, dst.data_ptr() + r0 * esz, stream)
+            dasp_b200.sumsq(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
+            if world > 1:
+                dist.all_reduce(norm2)
+            dasp_b200.scale_rsqrt(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
+            if world == 1:
+                return
+            if args.exchange == "bcast":
+                works = [dist.broadcast(dst[cuts[p]:cuts[p + 1]], src=p, async_op=True)
+                         for p in range(world) if cuts[p + 1] > cuts[p]]
+                for w in works:
+                    w.wait()
+            else:
+                dist.all_to_all_single(mine[:my_len], dst[r0:r1], output_split_sizes=recv_split, input_split_sizes=send_split)
+                dist.all_gather_into_tensor(dst, mine)
 
     def barrier():
         if world > 1:
@@ -525,6 +576,10 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         step(xa, xb)
         xa, xb = xb, xa
     xa[:m].copy_(x)
+    if fused:
+        for t_ in nrm:
+            t_.fill_(1.0)
+        fstate["k"] = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -536,6 +591,8 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     lam = float(torch.sqrt(norm2).item())
     chk = float(xa[:m].sum().item())
+    if fused and args.exchange in ("p2p", "mc"):  # the iterate is stored un-normalised there
+        chk /= lam
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     barrier()
@@ -553,6 +610,10 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
                    "partition": "nnz-balanced contiguous row slabs, x replicated",
                    "exchange": ("none (single GPU)" if world == 1 else
                                 "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if args.exchange == "bcast" else
+                                "fused: SpMV kernel stores y into every peer copy over NVLink P2P mappings; all_reduce(norm^2) only" if args.exchange == "p2p" else
+                                "fused: SpMV kernel stores y through one NVSwitch multicast mapping; all_reduce(norm^2) only" if args.exchange == "mc" else
+                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing through an NVSwitch multicast mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "mcu" else
+                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing to every peer mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "p2pu" else
                                 "all_reduce(norm^2) + NCCL all_to_all of slab pieces into P equal chunks + all_gather of the chunks"),
                    "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]},
         "spmv_only_ms": float(spmv_ms.item()), "exchange_and_vector_ms": step_ms - float(spmv_ms.item()),

@@ -173,6 +173,42 @@ int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, 
     return launch_spmv(h, d_x, d_y, permuted ? nullptr : h->L.order_rid, (cudaStream_t)stream, ab);
 }
 
+int dasp_spmv_scatter_to(dasp_handle *h, const void *d_x, void *const *d_dests, int n_dests, int64_t row_offset,
+                         const double *d_norm2, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || !d_dests || n_dests < 1 || n_dests > 8 || row_offset < 0) {
+        set_error("dasp_spmv_scatter_to: bad argument (1..8 destinations)");
+        return DASP_ERR_INVALID;
+    }
+    ScatterTo m{};
+    for (int p = 0; p < n_dests; p++) {
+        if (!d_dests[p]) { set_error("dasp_spmv_scatter_to: destination %d is NULL", p); return DASP_ERR_INVALID; }
+        if (p > 0) m.extra[p - 1] = d_dests[p];
+    }
+    m.n_extra = n_dests - 1;
+    m.row_offset = row_offset;
+    m.norm2 = d_norm2;
+    return launch_spmv(h, d_x, d_dests[0], h->L.order_rid, (cudaStream_t)stream, nullptr, &m);
+}
+
+int dasp_unpermute_to(dasp_handle *h, const void *d_y_perm, void *const *d_dests, int n_dests, int64_t row_offset,
+                      const double *d_norm2, void *stream)
+{
+    if (!h || (!d_y_perm && h->L.s.m > 0) || !d_dests || n_dests < 1 || n_dests > 8 || row_offset < 0) {
+        set_error("dasp_unpermute_to: bad argument (1..8 destinations)");
+        return DASP_ERR_INVALID;
+    }
+    ScatterTo m{};
+    for (int p = 0; p < n_dests; p++) {
+        if (!d_dests[p]) { set_error("dasp_unpermute_to: destination %d is NULL", p); return DASP_ERR_INVALID; }
+        if (p > 0) m.extra[p - 1] = d_dests[p];
+    }
+    m.n_extra = n_dests - 1;
+    m.row_offset = row_offset;
+    m.norm2 = d_norm2;
+    return unpermute_to(h, d_y_perm, m, d_dests[0], (cudaStream_t)stream);
+}
+
 // ---- checkpoint of the preprocessed layout ---------------------------------------------------------
 namespace {
 constexpr uint64_t kMagic = 0x3130305f50534144ull; // "DASP_001"

@@ -75,6 +75,7 @@ struct Layout {
     int *long_cbase = nullptr;              // [fill0_nnz_long / 32] same compact form for the long part
     unsigned short *long_cdelta = nullptr;  // [fill0_nnz_long]
     unsigned char *long_wide = nullptr;     // [n_long_units] in execution order
+    int *inv_order = nullptr;               // [m] inverse of order_rid, built on first use by dasp_unpermute_to
     unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
 };
 
@@ -106,11 +107,19 @@ namespace dasp {
 int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx,
                const void *d_val, cudaStream_t st);
 // spmv.cu
+// extra destinations of a fused-exchange product (dasp_spmv_scatter_to)
+struct ScatterTo {
+    void *extra[7];
+    int n_extra;
+    int64_t row_offset;
+    const double *norm2;
+};
 int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st,
-                const double *alpha_beta = nullptr);
+                const double *alpha_beta = nullptr, const ScatterTo *multi = nullptr);
 int save_layout(const dasp_handle *h, const char *path);
 int load_layout(dasp_handle *h, const char *path);
 int launches_per_spmv(const dasp_handle *h);
+int unpermute_to(dasp_handle *h, const void *d_y_perm, const ScatterTo &dst, void *first, cudaStream_t st);
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st);
 int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st);
 } // namespace dasp

@@ -48,6 +48,12 @@ struct SpmvArgs {
     const int *scatter; // nullptr: permuted order
     double alpha, beta; // y = alpha*A*x + beta*y when axpby != 0
     int axpby;
+    // fused exchange (dasp_spmv_scatter_to): the result is also stored into n_extra more vectors (peer GPUs' copies of
+    // the next x, or one NVSwitch multicast mapping), at element offset row_offset, scaled by 1/sqrt(*rs_ptr)
+    void *y_extra[7];
+    int n_extra;
+    long row_offset;
+    const double *rs_ptr;
     // long
     const void *long_val;
     const int *long_cid, *long_rpt_new, *unit_row, *unit_chunk, *unit_first;
@@ -197,7 +203,11 @@ __device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Ac
     T *y = static_cast<T *>(a.y);
     if (a.scatter) idx = a.scatter[idx];
     if (a.axpby) v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * to_acc(y[idx]) : A(0));
+    if (a.rs_ptr) v *= (A)rsqrt(__ldg(a.rs_ptr));
+    idx += a.row_offset;
     from_acc(y + idx, v);
+#pragma unroll 1
+    for (int p = 0; p < a.n_extra; p++) from_acc(static_cast<T *>(a.y_extra[p]) + idx, v); // P2P / multicast stores
 }
 
 template <typename A> __device__ __forceinline__ A warp_sum(A v)
@@ -808,6 +818,58 @@ __global__ void __launch_bounds__(256) scale_rsqrt(double *__restrict__ v, long 
 
 } // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) invert_order(const int *__restrict__ order, int m, int *__restrict__ inv)
+{
+    int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < m) inv[order[k]] = k;
+}
+
+struct UnpermArgs {
+    const void *y_perm;
+    const int *inv;
+    void *dest[8];
+    int n_dest;
+    long m, row_offset;
+    const double *rs_ptr;
+};
+
+// original row i (coalesced over i) <- y_perm[inv[i]] (scattered local read), scaled, stored to every destination
+template <typename T>
+__global__ void __launch_bounds__(256) unpermute_kernel(const __grid_constant__ UnpermArgs a)
+{
+    using A = typename Acc<T>::type;
+    const T *yp = static_cast<const T *>(a.y_perm);
+    const A f = a.rs_ptr ? (A)rsqrt(__ldg(a.rs_ptr)) : A(1);
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < a.m; i += (long)gridDim.x * 256L) {
+        const A v = to_acc(yp[__ldg(a.inv + i)]) * f;
+#pragma unroll 1
+        for (int p = 0; p < a.n_dest; p++) from_acc(static_cast<T *>(a.dest[p]) + a.row_offset + i, v);
+    }
+}
+} // namespace
+
+int unpermute_to(dasp_handle *h, const void *d_y_perm, const ScatterTo &dst, void *first, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const int m = L.s.m;
+    if (m == 0) return DASP_OK;
+    if (!L.inv_order) {
+        DASP_TRY(h->pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
+        invert_order<<<cdiv(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
+    }
+    UnpermArgs a{};
+    a.y_perm = d_y_perm; a.inv = L.inv_order; a.m = m; a.row_offset = (long)dst.row_offset; a.rs_ptr = dst.norm2;
+    a.dest[0] = first;
+    for (int p = 0; p < dst.n_extra; p++) a.dest[p + 1] = dst.extra[p];
+    a.n_dest = dst.n_extra + 1;
+    const int grid = min(cdiv(m, 256), (h->sm_count > 0 ? h->sm_count : 148) * 8);
+    if (h->dtype == DASP_F16) unpermute_kernel<__half><<<grid, 256, 0, st>>>(a);
+    else unpermute_kernel<double><<<grid, 256, 0, st>>>(a);
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
 int launches_per_spmv(const dasp_handle *) { return 1; }
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
@@ -830,7 +892,8 @@ int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream
     return DASP_OK;
 }
 
-int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st, const double *alpha_beta)
+int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st, const double *alpha_beta,
+                const ScatterTo *multi)
 {
     const Layout &L = h->L;
     const dasp_stats_t &s = L.s;
@@ -840,6 +903,12 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.axpby = alpha_beta ? 1 : 0;
     a.alpha = alpha_beta ? alpha_beta[0] : 1.0;
     a.beta = alpha_beta ? alpha_beta[1] : 0.0;
+    if (multi) {
+        a.n_extra = multi->n_extra;
+        for (int p = 0; p < multi->n_extra; p++) a.y_extra[p] = multi->extra[p];
+        a.row_offset = (long)multi->row_offset;
+        a.rs_ptr = multi->norm2;
+    }
     a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
     a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;

@@ -79,6 +79,8 @@ def load() -> C.CDLL:
         L.dasp_spmv.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_unpermuted.argtypes = [vp, vp, vp, vp]
         L.dasp_spmv_host.argtypes = [vp, vp, vp]
+        L.dasp_spmv_scatter_to.argtypes = [vp, vp, C.POINTER(vp), ip, C.c_int64, vp, vp]
+        L.dasp_unpermute_to.argtypes = [vp, vp, C.POINTER(vp), ip, C.c_int64, vp, vp]
         L.dasp_spmv_host_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
         L.dasp_spmv_axpby.argtypes = [vp, C.c_double, vp, C.c_double, vp, ip, vp]
         L.dasp_save.argtypes = [vp, C.c_char_p]
@@ -178,6 +180,20 @@ class Dasp:
         st = self.stats()
         self.dtype, self.m, self.n, self.nnz = st["dtype"], st["m"], st["n"], st["nnz"]
         return self
+
+    def spmv_scatter_to(self, d_x, dests, row_offset: int, d_norm2=None, stream: int = 0) -> None:
+        """Slab product in original row order, scaled by 1/sqrt(*d_norm2), stored at row_offset of every vector in
+        `dests` (device addresses: local, peer-mapped or multicast)."""
+        arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
+        _check(load().dasp_spmv_scatter_to(self._h, _ptr(d_x), arr, len(dests), row_offset, _ptr(d_norm2), C.c_void_p(stream)),
+               "dasp_spmv_scatter_to")
+
+    def unpermute_to(self, d_y_perm, dests, row_offset: int, d_norm2=None, stream: int = 0) -> None:
+        """Permuted slab product -> original order, scaled by 1/sqrt(*d_norm2), coalesced stores into every vector of
+        `dests` (local, peer-mapped or multicast device addresses) at row_offset."""
+        arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
+        _check(load().dasp_unpermute_to(self._h, _ptr(d_y_perm), arr, len(dests), row_offset, _ptr(d_norm2), C.c_void_p(stream)),
+               "dasp_unpermute_to")
 
     def spmv_timed(self, d_x, d_y, stream: int = 0, warmup: int = 0, reps: int = 1) -> float:
         """`reps` back-to-back launches issued from C; returns their total device time in ms."""

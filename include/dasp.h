@@ -176,6 +176,24 @@ int dasp_spmv_all_f16(const char *filename, const void *csrValA, const int *csrR
                       const int *csrColIdxA, const void *X_val, void *Y_val, int *order_rid,
                       int rowA, int colA, int nnzA, int NUM, double threshold, int block_longest);
 
+/* Fused product + exchange for the row-partitioned iterated workload: this GPU's slab product, in ORIGINAL row order
+ * and scaled by 1/sqrt(*d_norm2) when d_norm2 != NULL (device scalar, e.g. the all-reduced squared norm of the
+ * previous iterate), is stored by the SpMV kernel itself at element offset row_offset of EVERY vector in d_dests
+ * (1..8 device pointers): this GPU's copy of the next x and the peer GPUs' copies mapped into this process (CUDA IPC /
+ * symmetric memory), or a single NVSwitch multicast mapping of all copies.  The stores travel over NVLink while the
+ * rest of the slab is still being multiplied; no separate all-gather / broadcast is needed, only a barrier (the
+ * all-reduce of the next norm) before the vectors are read.  FP64 and FP16. */
+int dasp_spmv_scatter_to(dasp_handle *h, const void *d_x, void *const *d_dests, int n_dests, int64_t row_offset,
+                         const double *d_norm2, void *stream);
+
+/* The exchange step of the iterated workload as ONE coalesced pass: y (this GPU's slab product in PERMUTED order, as
+ * dasp_spmv leaves it) is read through the inverse permutation, scaled by 1/sqrt(*d_norm2) when d_norm2 != NULL and
+ * stored in ORIGINAL row order, fully coalesced, at element offset row_offset of every vector in d_dests (local, peer
+ * mapped, or one NVSwitch multicast mapping: then every 256-byte warp store is replicated to all GPUs by the switch).
+ * Replaces un-permute + scale + all-gather/broadcast. */
+int dasp_unpermute_to(dasp_handle *h, const void *d_y_perm, void *const *d_dests, int n_dests, int64_t row_offset,
+                      const double *d_norm2, void *stream);
+
 /* Vector helpers of the iterated (power-iteration) workload, x <- A x / ||A x||_2 (north_star; the
  * reference has no iterated driver).  All pointers are device pointers, FP64 only.
  *   dasp_sumsq:  *d_out = sum_i v[i]^2           (deterministic two-stage reduction)

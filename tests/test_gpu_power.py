@@ -51,3 +51,53 @@ def test_sumsq_large_and_empty(cuda_device):
     dasp_b200.sumsq(v, 0, out, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert out.item() == 0.0
+
+
+def test_scatter_to_several_destinations(cuda_device):
+    """The fused-exchange entry on one GPU: the slab product lands, scaled, at row_offset of every destination."""
+    import torch
+
+    import dasp_b200
+
+    m, n, rp, ci, v = get("symmetric_like")
+    x0 = x_for(n)
+    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, n, rp, ci, v)
+    s = torch.cuda.current_stream().cuda_stream
+    dx = torch.from_numpy(x0).to(cuda_device)
+    norm2 = torch.tensor([6.25], dtype=torch.float64, device=cuda_device)
+    off = 17
+    dests = [torch.full((m + 40,), -7.0, dtype=torch.float64, device=cuda_device) for _ in range(3)]
+    h.spmv_scatter_to(dx, dests, off, norm2, s)
+    torch.cuda.synchronize()
+    want = oracle.csr_spmv_f64(m, rp, ci, v, x0) / 2.5
+    for d in dests:
+        got = d.cpu().numpy()
+        assert np.all(got[:off] == -7.0) and np.all(got[off + m:] == -7.0)
+        assert np.linalg.norm(got[off:off + m] - want) <= 1e-12 * np.linalg.norm(want)
+    h.spmv_scatter_to(dx, dests[:1], 0, None, s)
+    torch.cuda.synchronize()
+    assert np.linalg.norm(dests[0].cpu().numpy()[:m] - want * 2.5) <= 1e-12 * np.linalg.norm(want * 2.5)
+    h.close()
+
+
+def test_unpermute_to_matches_unpermuted_product(cuda_device):
+    import torch
+
+    import dasp_b200
+
+    m, n, rp, ci, v = get("mixed_f1")
+    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, n, rp, ci, v)
+    s = torch.cuda.current_stream().cuda_stream
+    dx = torch.from_numpy(x_for(n)).to(cuda_device)
+    yp = torch.zeros(m, dtype=torch.float64, device=cuda_device)
+    yo = torch.zeros(m, dtype=torch.float64, device=cuda_device)
+    h.spmv(dx, yp, s)
+    h.spmv_unpermuted(dx, yo, s)
+    norm2 = torch.tensor([16.0], dtype=torch.float64, device=cuda_device)
+    dests = [torch.full((m + 9,), 3.0, dtype=torch.float64, device=cuda_device) for _ in range(2)]
+    for rep in range(2):
+        h.unpermute_to(yp, dests, 5, norm2, s)
+    torch.cuda.synchronize()
+    for d in dests:
+        assert bool(torch.equal(d[5:5 + m], yo * 0.25)) and bool((d[:5] == 3.0).all()) and bool((d[5 + m:] == 3.0).all())
+    h.close()
