@@ -202,12 +202,14 @@ __device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Ac
     using A = typename Acc<T>::type;
     T *y = static_cast<T *>(a.y);
     if (a.scatter) idx = a.scatter[idx];
-    if (a.axpby) v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * to_acc(y[idx]) : A(0));
-    if (a.rs_ptr) v *= (A)rsqrt(__ldg(a.rs_ptr));
-    idx += a.row_offset;
-    from_acc(y + idx, v);
+    if (a.axpby) { // one flag for every non-default form: alpha/beta, 1/sqrt(norm^2) scaling, offset, extra destinations
+        v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * to_acc(y[idx]) : A(0));
+        if (a.rs_ptr) v *= (A)rsqrt(__ldg(a.rs_ptr));
+        idx += a.row_offset;
 #pragma unroll 1
-    for (int p = 0; p < a.n_extra; p++) from_acc(static_cast<T *>(a.y_extra[p]) + idx, v); // P2P / multicast stores
+        for (int p = 0; p < a.n_extra; p++) from_acc(static_cast<T *>(a.y_extra[p]) + idx, v); // P2P / multicast stores
+    }
+    from_acc(y + idx, v);
 }
 
 template <typename A> __device__ __forceinline__ A warp_sum(A v)
@@ -900,7 +902,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const bool f16 = h->dtype == DASP_F16;
     SpmvArgs a{};
     a.x = d_x; a.y = d_y; a.scatter = scatter;
-    a.axpby = alpha_beta ? 1 : 0;
+    a.axpby = (alpha_beta || multi) ? 1 : 0;
     a.alpha = alpha_beta ? alpha_beta[0] : 1.0;
     a.beta = alpha_beta ? alpha_beta[1] : 0.0;
     if (multi) {
