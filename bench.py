@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-index-compression", action="store_true", help="A/B aid: kernels read reg_cid instead of the compact 16-bit indices")
     ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
-    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a", "p2p", "mc", "mcu", "p2pu"],
+    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a", "p2p", "mc", "mcu", "p2pu", "mcc", "p2pc"],
                     help="power iteration: how the y slabs reach every rank (bcast: one NCCL broadcast per slab; a2a: all-to-all "
                          "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs; p2p / mc: fused, the "
                          "SpMV kernel stores y straight into every peer's next x through NVLink peer mappings / one NVSwitch "
@@ -501,7 +501,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     recv_split = [overlap(cuts[p], cuts[p + 1], rank * chunk, min(m, (rank + 1) * chunk)) for p in range(world)]
     my_len = sum(recv_split)
 
-    fused = args.exchange in ("p2p", "mc", "mcu", "p2pu") and world > 1
+    fused = args.exchange in ("p2p", "mc", "mcu", "p2pu", "mcc", "p2pc") and world > 1
     if fused:
         # Fused product + exchange: both iterates live in symmetric memory; every rank's kernel stores its slab of y
         # into ALL copies of the next iterate (peer mappings or one multicast mapping).  The vector is kept
@@ -516,8 +516,9 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         xa[:m].copy_(x)
         hdl.barrier()
         peer = [int(p) for p in hdl.buffer_ptrs]
-        use_mc = args.exchange in ("mc", "mcu")
-        two_pass = args.exchange in ("mcu", "p2pu")
+        use_mc = args.exchange in ("mc", "mcu", "mcc")
+        two_pass = args.exchange in ("mcu", "p2pu", "mcc", "p2pc")
+        copy_pass = args.exchange in ("mcc", "p2pc")
         yp = torch.zeros(max(r1 - r0, 1), dtype=torch.float64, device=dev) if two_pass else None
         token = torch.zeros(1, dtype=torch.float32, device=dev)
         mc_ptr = int(hdl.multicast_ptr) if use_mc else 0
@@ -536,11 +537,18 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         def step(src, dst):
             k = fstate["k"]
             if two_pass:
-                # permuted (coalesced) product, norm, then ONE coalesced un-permute + scale + store-to-all pass
-                h.spmv(src, yp, stream)
-                dasp_b200.sumsq(yp, r1 - r0, norm2, stream)
-                dist.all_reduce(norm2)
-                h.unpermute_to(yp, dests_of(dst), r0, norm2, stream)
+                if copy_pass:
+                    # product scattered to original order LOCALLY, norm, then one coalesced scale + copy-to-all pass
+                    h.spmv_unpermuted(src, yp, stream)
+                    dasp_b200.sumsq(yp, r1 - r0, norm2, stream)
+                    dist.all_reduce(norm2)
+                    dasp_b200.scale_copy_to(yp, r1 - r0, dests_of(dst), r0, norm2, stream)
+                else:
+                    # permuted (coalesced) product, norm, then ONE coalesced un-permute + scale + store-to-all pass
+                    h.spmv(src, yp, stream)
+                    dasp_b200.sumsq(yp, r1 - r0, norm2, stream)
+                    dist.all_reduce(norm2)
+                    h.unpermute_to(yp, dests_of(dst), r0, norm2, stream)
                 dist.all_reduce(token)  # orders every rank's stores into this rank's copy before the next product reads it
                 return
             # y_k = A x_k / ||y_{k-1}||  (x_k is stored un-normalised); the first step scales by 1
@@ -614,6 +622,8 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
                                 "fused: SpMV kernel stores y through one NVSwitch multicast mapping; all_reduce(norm^2) only" if args.exchange == "mc" else
                                 "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing through an NVSwitch multicast mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "mcu" else
                                 "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing to every peer mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "p2pu" else
+                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing through an NVSwitch multicast mapping (dasp_scale_copy_to) + token all_reduce" if args.exchange == "mcc" else
+                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing to every peer mapping (dasp_scale_copy_to) + token all_reduce" if args.exchange == "p2pc" else
                                 "all_reduce(norm^2) + NCCL all_to_all of slab pieces into P equal chunks + all_gather of the chunks"),
                    "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]},
         "spmv_only_ms": float(spmv_ms.item()), "exchange_and_vector_ms": step_ms - float(spmv_ms.item()),

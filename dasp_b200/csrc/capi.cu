@@ -526,6 +526,18 @@ int dasp_scale_rsqrt(double *d_v, int64_t count, const double *d_norm2, void *st
     return scale_by_rsqrt(d_v, count, d_norm2, (cudaStream_t)stream);
 }
 
+int dasp_scale_copy_to(const double *d_v, int64_t count, void *const *d_dests, int n_dests, int64_t offset, const double *d_norm2,
+                       void *stream)
+{
+    if ((!d_v && count > 0) || count < 0 || !d_dests || n_dests < 1 || n_dests > 8 || offset < 0) {
+        set_error("dasp_scale_copy_to: bad argument (1..8 destinations)");
+        return DASP_ERR_INVALID;
+    }
+    for (int p = 0; p < n_dests; p++)
+        if (!d_dests[p]) { set_error("dasp_scale_copy_to: destination %d is NULL", p); return DASP_ERR_INVALID; }
+    return scale_copy_to(d_v, count, d_dests, n_dests, offset, d_norm2, (cudaStream_t)stream);
+}
+
 int dasp_partition_rows(int m, const int *rowptr, int parts, int *cuts)
 {
     if (m < 0 || !rowptr || parts < 1 || !cuts) { set_error("dasp_partition_rows: bad argument"); return DASP_ERR_INVALID; }

@@ -122,4 +122,6 @@ int launches_per_spmv(const dasp_handle *h);
 int unpermute_to(dasp_handle *h, const void *d_y_perm, const ScatterTo &dst, void *first, cudaStream_t st);
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st);
 int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st);
+int scale_copy_to(const double *d_v, int64_t count, void *const *dests, int n_dests, int64_t offset, const double *d_norm2,
+                  cudaStream_t st);
 } // namespace dasp

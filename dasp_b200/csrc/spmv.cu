@@ -887,6 +887,54 @@ int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
     return DASP_OK;
 }
 
+namespace {
+struct CopyToArgs {
+    const double *src;
+    void *dest[8];
+    int n_dest;
+    long n, offset;
+    const double *norm2;
+    int vec_ok;
+};
+__global__ void __launch_bounds__(256) scale_copy_kernel(const __grid_constant__ CopyToArgs a)
+{
+    const double f = a.norm2 ? 1.0 / sqrt(*a.norm2) : 1.0;
+    // two doubles per thread when everything is 16-byte aligned (128-bit multicast / peer stores)
+    const bool vec = a.vec_ok && ((a.offset | a.n) & 1) == 0 && ((uintptr_t)a.src & 15) == 0;
+    if (vec) {
+        const long n2 = a.n >> 1;
+        for (long i = blockIdx.x * 256L + threadIdx.x; i < n2; i += (long)gridDim.x * 256L) {
+            double2 v = reinterpret_cast<const double2 *>(a.src)[i];
+            v.x *= f; v.y *= f;
+#pragma unroll 1
+            for (int p = 0; p < a.n_dest; p++) reinterpret_cast<double2 *>(static_cast<double *>(a.dest[p]) + a.offset)[i] = v;
+        }
+    } else {
+        for (long i = blockIdx.x * 256L + threadIdx.x; i < a.n; i += (long)gridDim.x * 256L) {
+            const double v = a.src[i] * f;
+#pragma unroll 1
+            for (int p = 0; p < a.n_dest; p++) static_cast<double *>(a.dest[p])[a.offset + i] = v;
+        }
+    }
+}
+} // namespace
+
+int scale_copy_to(const double *d_v, int64_t count, void *const *dests, int n_dests, int64_t offset, const double *d_norm2,
+                  cudaStream_t st)
+{
+    if (count <= 0) return DASP_OK;
+    CopyToArgs a{};
+    a.src = d_v; a.n = (long)count; a.offset = (long)offset; a.norm2 = d_norm2; a.n_dest = n_dests;
+    a.vec_ok = 1;
+    for (int p = 0; p < n_dests; p++) {
+        a.dest[p] = dests[p];
+        if ((uintptr_t)dests[p] & 15) a.vec_ok = 0; // 128-bit stores need 16-byte aligned destinations
+    }
+    scale_copy_kernel<<<RED_CTAS * 2, 256, 0, st>>>(a);
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
 int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream_t st)
 {
     if (count > 0) scale_rsqrt<<<RED_CTAS * 2, 256, 0, st>>>(d_v, (long)count, d_norm2);

@@ -107,6 +107,7 @@ def load() -> C.CDLL:
         L.dasp_free_host.restype = None
         L.dasp_sumsq.argtypes = [vp, C.c_int64, vp, vp]
         L.dasp_scale_rsqrt.argtypes = [vp, C.c_int64, vp, vp]
+        L.dasp_scale_copy_to.argtypes = [vp, C.c_int64, C.POINTER(vp), ip, C.c_int64, vp, vp]
         _lib = L
     return _lib
 
@@ -323,3 +324,10 @@ def read_mtx(path: str, dtype: int = DASP_F64):
         for p in (rp, ci, va):
             L.dasp_free_host(p)
     return m.value, n.value, rowptr, colidx, val, bool(sym.value)
+
+
+def scale_copy_to(d_v, count: int, dests, offset: int, d_norm2=None, stream: int = 0) -> None:
+    """dest_p[offset + i] = v[i] / sqrt(*d_norm2) for every destination (local / peer / multicast addresses)."""
+    arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
+    _check(load().dasp_scale_copy_to(_ptr(d_v), count, arr, len(dests), offset, _ptr(d_norm2), C.c_void_p(stream)),
+           "dasp_scale_copy_to")

@@ -200,6 +200,10 @@ int dasp_unpermute_to(dasp_handle *h, const void *d_y_perm, void *const *d_dests
  *   dasp_scale_rsqrt: v[i] *= 1/sqrt(*d_norm2)   (d_norm2 stays on the device: no host round trip) */
 int dasp_sumsq(const double *d_v, int64_t count, double *d_out, void *stream);
 int dasp_scale_rsqrt(double *d_v, int64_t count, const double *d_norm2, void *stream);
+/*   dasp_scale_copy_to: dest_p[offset + i] = v[i] / sqrt(*d_norm2) for every destination p (1..8 device pointers:
+ *   local, peer-mapped, or one NVSwitch multicast mapping) — scale + broadcast of a slab as one coalesced pass */
+int dasp_scale_copy_to(const double *d_v, int64_t count, void *const *d_dests, int n_dests, int64_t offset,
+                       const double *d_norm2, void *stream);
 
 /* Matrix Market coordinate file -> host CSR, with the reference reader's exact semantics
  * (mmio_allinone, src/mmio_highlevel.h:608-774) so that a file produces the identical CSR and therefore the

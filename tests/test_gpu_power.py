@@ -101,3 +101,20 @@ def test_unpermute_to_matches_unpermuted_product(cuda_device):
     for d in dests:
         assert bool(torch.equal(d[5:5 + m], yo * 0.25)) and bool((d[:5] == 3.0).all()) and bool((d[5 + m:] == 3.0).all())
     h.close()
+
+
+@pytest.mark.parametrize("count,offset", [(1000, 6), (1001, 6), (1000, 7), (1, 0), (0, 3)])
+def test_scale_copy_to(cuda_device, count, offset):
+    import torch
+
+    import dasp_b200
+
+    s = torch.cuda.current_stream().cuda_stream
+    v = torch.arange(1, count + 1, dtype=torch.float64, device=cuda_device)
+    norm2 = torch.tensor([4.0], dtype=torch.float64, device=cuda_device)
+    dests = [torch.full((count + 16,), -1.0, dtype=torch.float64, device=cuda_device) for _ in range(3)]
+    dasp_b200.scale_copy_to(v if count else dests[0], count, dests, offset, norm2, s)
+    torch.cuda.synchronize()
+    for d in dests:
+        assert bool(torch.equal(d[offset:offset + count], v * 0.5))
+        assert bool((d[:offset] == -1.0).all()) and bool((d[offset + count:] == -1.0).all())
