@@ -269,7 +269,7 @@ def run_ours(args):
     create_s = time.perf_counter() - t0
     st = h.stats()
     var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3, "tma": 4}[args.variant]
-    h.set_variant(0 if var == 4 else var, 0 if var == 3 else var, 0)
+    h.set_variant(0 if var == 4 else var, 0 if var == 3 else var, var if var == 2 else 0)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)

@@ -682,7 +682,9 @@ __device__ __forceinline__ long paired_y(int G, long tile, int r, int h)
 }
 
 // MODE 0: 1&3 tiles   MODE 1: 3/4 rows   MODE 2: 2&2 tiles
-template <typename T, int MODE, bool KEEP>
+// SMMA: the reference's formulation (src/dasp_f64.h:296-483): one DMMA m8n8k4 per 8x4 tile with B masked to the slots
+// that belong to the first / second row of a tile row; the useful results sit on the diagonal of C.
+template <typename T, int MODE, bool KEEP, bool SMMA>
 __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
@@ -706,9 +708,41 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
         v[j] = ok ? ld_stream1(val + s, pol) : T(0);
         c[j] = ok ? ld_stream1(cid + s, pol) : 0;
     }
+    const int r = lane >> 2, q = lane & 3;
+    if constexpr (SMMA && sizeof(T) == 8) {
+        // lane = slot: A[r][q] = value, B[q][r] = x of the same slot (masked), C[r][r] = dot product of tile row r.
+        // C[r][r] is held by lane 4r + (r>>1) in register r&1: that lane stores it, no shuffle.
+        const bool holder = q == (r >> 1);
+#pragma unroll
+        for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
+            const long tile = tile0 + j;
+            const double av = (double)to_acc(v[j]);
+            const double xg = (double)gather(x, c[j]);
+            double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+            if (MODE == 1) {
+                dmma884(c0, av, xg);
+                const long row = tile * 8 + r;
+                if (holder && row < nrows) store_y<T>(a, a.y34 + row, (A)c0[r & 1]);
+            } else {
+                const bool first = MODE == 0 ? q == 0 : q < 2; // slots of the first row of the tile row
+                dmma884(c0, av, first ? xg : 0.0);
+                dmma884(c1, av, first ? 0.0 : xg);
+                if (MODE == 0) {
+                    if (holder && tile * 8 + r < nrows) {
+                        store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), (A)c0[r & 1]);
+                        store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), (A)c1[r & 1]);
+                    }
+                } else if (holder) {
+                    const long y0 = paired_y(a.G, tile, r, 0), y1 = paired_y(a.G, tile, r, 1);
+                    if (y0 < nrows) store_y<T>(a, a.y22 + y0, (A)c0[r & 1]);
+                    if (y1 < nrows) store_y<T>(a, a.y22 + y1, (A)c1[r & 1]);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
-    const int r = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
         const long tile = tile0 + j;
@@ -743,7 +777,7 @@ __device__ __forceinline__ void zero_rows(const SpmvArgs &a, long w)
 
 // MED: 0 one lane per row (large matrices), 1 DMMA tiles, 2 four lanes per row (small matrices)
 // KEEP: the layout fits in L2, streams stay at normal L2 priority (small matrices iterated back to back)
-template <typename T, int MED, int LONGV, bool KEEP>
+template <typename T, int MED, int LONGV, bool KEEP, bool SMMA>
 __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w, unsigned char *smem)
 {
     switch (cat) {
@@ -753,15 +787,15 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
         else medium_rows<T, MED == 1, KEEP>(a, w);
         break;
     case 2: short_singles<T, KEEP>(a, w); break;
-    case 3: short_tiles<T, 0, KEEP>(a, w); break;
-    case 4: short_tiles<T, 1, KEEP>(a, w); break;
-    case 5: short_tiles<T, 2, KEEP>(a, w); break;
+    case 3: short_tiles<T, 0, KEEP, SMMA>(a, w); break;
+    case 4: short_tiles<T, 1, KEEP, SMMA>(a, w); break;
+    case 5: short_tiles<T, 2, KEEP, SMMA>(a, w); break;
     default: zero_rows<T>(a, w); break;
     }
 }
 
 // One warp per work item; the block index selects the category (grid = sum of the per-category CTA counts).
-template <typename T, int MED, int LONGV, bool KEEP>
+template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false>
 __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
@@ -774,7 +808,7 @@ __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __
     const int local = bid - first;
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
     if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
-    run_category<T, MED, LONGV, KEEP>(a, cat, (long)local * WARPS + warp, dyn_smem);
+    run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * WARPS + warp, dyn_smem);
 }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -996,6 +1030,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     else if (h->var_medium == DASP_VARIANT_SPLIT) med = 2;
     const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
     const bool tma_long = h->var_long == DASP_VARIANT_TMA;
+    const bool mma_short = !f16 && h->var_short == DASP_VARIANT_MMA;
     a.items[0] = on_long * (long)L.n_long_units;
     a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);
     a.items[2] = on_short * (long)cdiv(s.short_row_1, 32 * SINGLES_PER_THREAD);
@@ -1014,7 +1049,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const int grid = a.e[6];
 
     // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
-    const bool keep = small && med != 1 && !mma_long && !tma_long;
+    const bool keep = small && med != 1 && !mma_long && !tma_long && !mma_short;
     // the kernels that use no shared memory ask for the whole unified array as L1 (x gathers live there), as the
     // reference does (src/dasp_f64.h:1280-1283)
 #define DASP_LAUNCH(T, MED, LV, KEEP)                                                                              \
@@ -1039,6 +1074,9 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
         else if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, 0, true); else DASP_LAUNCH(__half, 2, 0, false); }
         else { if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
+    } else if (mma_short) { // DMMA short rows (comparison variant): with the plain or the DMMA long / medium paths
+        if (med == 1 && mma_long) spmv_kernel<double, 1, 1, false, true><<<grid, CTA, 0, st>>>(a);
+        else spmv_kernel<double, 0, 0, false, true><<<grid, CTA, 0, st>>>(a);
     } else if (tma_long) {
         DASP_LAUNCH(double, 0, 2, false);
     } else if (mma_long) {

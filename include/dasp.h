@@ -146,6 +146,8 @@ int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *o
 int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes,
                 int64_t *bytes);
 
+/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA;  short_rows: AUTO | CUDA_CORE | MMA
+ * (FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 
 /* The medium-row kernels read a compact resident copy of the regular part's column indices (per 8x4 tile one

@@ -68,9 +68,10 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         dx = torch.from_numpy(x).to(cuda_device)
         for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA]
                         if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA]):
-            # medium: cuda/mma/split; long: cuda/mma/tma (a variant that does not apply to a category = cuda-core)
+            # medium: cuda/mma/split; long: cuda/mma/tma; short: cuda/mma (a variant that does not apply = cuda-core)
             h.set_variant(variant if variant != dasp.VARIANT_TMA else dasp.VARIANT_CUDA_CORE,
-                          variant if variant != dasp.VARIANT_SPLIT else dasp.VARIANT_CUDA_CORE, dasp.VARIANT_AUTO)
+                          variant if variant != dasp.VARIANT_SPLIT else dasp.VARIANT_CUDA_CORE,
+                          variant if variant == dasp.VARIANT_MMA else dasp.VARIANT_AUTO)
             for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
                 dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
                 h.spmv(dx, dy, torch.cuda.current_stream().cuda_stream)
