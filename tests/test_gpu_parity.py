@@ -283,3 +283,30 @@ def test_spmv_is_cuda_graph_capturable(dasp, cuda_device):
     torch.cuda.synchronize()
     assert bool(torch.equal(y_graph, y_direct))
     h.close()
+
+
+def test_c_example_runs_against_the_abi(dasp, cuda_device, tmp_path):
+    """examples/spmv_mtx.c (the reference's command line rewritten on the C ABI) builds with gcc against include/dasp.h,
+    reads a Matrix Market file, runs and verifies itself against the serial CSR loop."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "spmv_mtx")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "spmv_mtx.c"),
+                           "-L", os.path.join(root, "dasp_b200"), "-ldasp_b200", "-Wl,-rpath," + os.path.join(root, "dasp_b200"),
+                           "-lm", "-o", exe])
+    m, n, rp, ci, v = get("mixed_f1")
+    mtx = tmp_path / "f1.mtx"
+    with open(mtx, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write("%d %d %d\n" % (m, n, int(rp[m])))
+        for i in range(m):
+            for j in range(rp[i], rp[i + 1]):
+                f.write("%d %d %.17g\n" % (i + 1, ci[j] + 1, v[j]))
+    for extra in ([], ["-ones"]):
+        p = subprocess.run([exe, str(mtx), "20"] + extra, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert "PASS" in p.stdout and "SpMV_X" in p.stdout
+        rec = [l for l in p.stdout.splitlines() if l.startswith("record: ")][0][len("record: "):].split(",")
+        assert rec[1:4] == [str(m), str(n), str(int(rp[m]))]
