@@ -689,45 +689,53 @@ def other_configs(args, dev):
 
 
 def reference_kernels_leg(args, dev):
-    """The reference's own kernels (unmodified, recompiled for sm_100a: oracle/_ref) and ours on the same
-    bounded sample: a 128^3 stencil (the reference preprocesses on one host thread)."""
+    """The reference's own kernels (unmodified, recompiled for sm_100a: oracle/_ref) and ours on the same bounded
+    samples: a 128^3 stencil (the reference preprocesses on one host thread) and the cop20k_A stand-in in FP64 (C1)
+    and FP16 (C2).  The reference times itself (100 warm-up + 1000 launches, gettimeofday, src/dasp_f64.h:1285-1320);
+    ours is timed with the same protocol from C (dasp_spmv_timed)."""
     import torch
 
     import dasp_b200
     import oracle
     from dasp_b200 import synth
 
-    if not oracle.ref_available(oracle.F64):
+    if not (oracle.ref_available(oracle.F64) and oracle.ref_available(oracle.F16)):
         return {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+    out = {}
     g = min(args.grid, 128)
-    spec = synth.stencil27(g)
-    rp, ci, v, nnz = synth.generate(spec, 0, spec.m, dev)
-    rp_h, ci_h, v_h = rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy()
-    m = int(spec.m)
-    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, m, rp, ci, v, nnz=nnz)
-    x = torch.ones(m, dtype=torch.float64, device=dev)
-    y = torch.empty(m, dtype=torch.float64, device=dev)
+    samples = [("stencil", synth.stencil27(g), False, f"27-point stencil {g}^3 fp64"),
+               ("c1", synth.banded(), False, "cop20k_A stand-in fp64"),
+               ("c2", synth.banded(), True, "cop20k_A stand-in fp16")]
     s = torch.cuda.current_stream(dev).cuda_stream
-    for _ in range(20):
-        h.spmv(x, y, s)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(200):
-        h.spmv(x, y, s)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ours_ms = e0.elapsed_time(e1) / 200
-    h.close()
-    del rp, ci, v
-    r = oracle.ref_spmv_all(oracle.F64, m, m, rp_h, ci_h, v_h, x=np.ones(m))
-    cols = r["csv"].split(",")
-    ref_ms = float(cols[21])  # dasp_time of the CSV record, src/dasp_f64.h:1441
-    y_ref = oracle.csr_spmv_f64(m, rp_h, ci_h, v_h, np.ones(m))
-    ref_err = float(np.linalg.norm(r["y_perm"] - y_ref[r["order_rid"]]) / np.linalg.norm(y_ref)) if r["ran_on_gpu"] else None
-    return {"sample": f"27-point stencil {g}^3 ({nnz} nnz), reference protocol: 100 warm + 1000 timed launches, gettimeofday",
-            "ref_ms": ref_ms, "ref_gflops": 2.0 * nnz / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else None,
-            "ours_ms": ours_ms, "ours_gflops": 2.0 * nnz / (ours_ms * 1e-3) / 1e9,
-            "ran_on_gpu": r["ran_on_gpu"], "ref_y_rel_l2_vs_serial_csr": ref_err}
+    for key, spec, half, label in samples:
+        try:
+            m = int(spec.m)
+            dt = oracle.F16 if half else oracle.F64
+            tdt = torch.float16 if half else torch.float64
+            rp, ci, v, nnz = synth.generate(spec, 0, m, dev, half=half)
+            rp_h, ci_h, v_h = rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy()
+            h = dasp_b200.Dasp(dasp_b200.DASP_F16 if half else dasp_b200.DASP_F64, m, m, rp, ci, v, nnz=nnz)
+            x = torch.ones(m, dtype=tdt, device=dev)
+            y = torch.empty(m, dtype=tdt, device=dev)
+            ours_ms = h.spmv_timed(x, y, s, 100, 1000) / 1000
+            h.close()
+            del rp, ci, v
+            xs = np.ones(m, dtype=np.float16 if half else np.float64)
+            r = oracle.ref_spmv_all(dt, m, m, rp_h, ci_h, v_h, x=xs)
+            cols = r["csv"].split(",")
+            ref_ms = float(cols[22 if half else 21])  # dasp_time of the CSV record (src/dasp_f64.h:1441, src/dasp_f16.h:1758)
+            f = oracle.csr_spmv_f16 if half else oracle.csr_spmv_f64
+            y_ref = f(m, rp_h, ci_h, v_h, xs)
+            ref_err = (float(np.linalg.norm(r["y_perm"].astype(np.float64) - y_ref[r["order_rid"]]) / np.linalg.norm(y_ref))
+                       if r["ran_on_gpu"] else None)
+            out[key] = {"sample": f"{label} ({nnz} nnz); both timed as 100 warm-up + 1000 back-to-back launches",
+                        "ref_ms": ref_ms, "ref_gflops": 2.0 * nnz / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else None,
+                        "ours_ms": ours_ms, "ours_gflops": 2.0 * nnz / (ours_ms * 1e-3) / 1e9,
+                        "speedup": ref_ms / ours_ms if ours_ms > 0 else None,
+                        "ran_on_gpu": r["ran_on_gpu"], "ref_y_rel_l2_vs_serial_csr": ref_err}
+        except Exception as e:
+            out[key] = {"error": repr(e)}
+    return out
 
 
 def main():
