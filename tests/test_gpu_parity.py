@@ -310,3 +310,32 @@ def test_c_example_runs_against_the_abi(dasp, cuda_device, tmp_path):
         assert "PASS" in p.stdout and "SpMV_X" in p.stdout
         rec = [l for l in p.stdout.splitlines() if l.startswith("record: ")][0][len("record: "):].split(",")
         assert rec[1:4] == [str(m), str(n), str(int(rp[m]))]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_layout_and_product(dasp, cuda_device, seed):
+    """Random row-length mixes, duplicate / unsorted columns, random threshold and block_longest: GPU preprocessing
+    bit-exact vs the oracle and y within tolerance, FP64 and FP16."""
+    import torch
+    from fuzz import random_case
+
+    m, n, rp, ci, v, threshold, block_longest = random_case(seed)
+    for dtype in (oracle.F64, oracle.F16):
+        npdt = np.float16 if dtype == oracle.F16 else np.float64
+        vv = v.astype(npdt)
+        ref = oracle.preprocess(dtype, m, n, rp, ci, vv, threshold, block_longest)
+        h = dasp.Dasp(dtype, m, n, rp, ci, vv, threshold=threshold, block_longest=block_longest)
+        for a in dasp.lib.ARRAYS:
+            assert np.array_equal(h.export(a).view(np.uint8), ref[a].view(np.uint8)), f"seed {seed}: {a}"
+        x = x_for(n, seed=seed).astype(npdt)
+        dx = torch.from_numpy(x).to(cuda_device)
+        dy = torch.full((m,), float("nan"), dtype=dx.dtype, device=cuda_device)
+        h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        f = oracle.csr_spmv_f16 if dtype == oracle.F16 else oracle.csr_spmv_f64
+        y_ref = f(m, rp, ci, vv, x)
+        got = dy.cpu().numpy().astype(np.float64)
+        assert np.all(np.isfinite(got))
+        scale = max(np.linalg.norm(y_ref), 1e-300)
+        assert np.linalg.norm(got - y_ref) / scale <= (FP64_TOL if dtype == oracle.F64 else 4e-3), f"seed {seed}"
+        h.close()

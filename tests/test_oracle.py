@@ -198,3 +198,20 @@ def test_oracle_matches_compiled_reference_with_other_parameters(threshold, bloc
         r = _defined(oracle.ref_spmv_all(dtype, m, n, rp, ci, vv, threshold=threshold, block_longest=block_longest))
         for a in ARRAYS:
             assert np.array_equal(o[a].view(np.uint8), r[a].view(np.uint8)), f"{name}: {a}"
+
+
+@pytest.mark.skipif(not (oracle.ref_available(oracle.F64) and oracle.ref_available(oracle.F16)),
+                    reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_fuzz_against_compiled_reference(seed):
+    """Random row-length mixes, duplicate / unsorted columns, random threshold and block_longest: restatement ==
+    compiled reference, bit for bit, both precisions."""
+    from fuzz import random_case
+
+    m, n, rp, ci, v, threshold, block_longest = random_case(seed)
+    for dtype in (oracle.F64, oracle.F16):
+        vv = _val(v, dtype)
+        o = _defined(oracle.preprocess(dtype, m, n, rp, ci, vv, threshold, block_longest))
+        r = _defined(oracle.ref_spmv_all(dtype, m, n, rp, ci, vv, threshold=threshold, block_longest=block_longest))
+        for a in ARRAYS:
+            assert np.array_equal(o[a].view(np.uint8), r[a].view(np.uint8)), f"seed {seed} dtype {dtype}: {a}"
