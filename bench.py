@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--half", action="store_true", help="run the chosen workload in FP16 (values and x rounded to half)")
     ap.add_argument("--no-index-compression", action="store_true", help="A/B aid: kernels read reg_cid instead of the compact 16-bit indices")
     ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
@@ -247,6 +248,8 @@ def run_ours(args):
     dasp_b200.load()
 
     spec, wname, half = make_spec(args)
+    if args.half and not half:
+        half, wname = True, wname.replace("fp64", "fp16")
     esz = 2 if half else 8
     tdt = torch.float16 if half else torch.float64
     dtype = dasp_b200.DASP_F16 if half else dasp_b200.DASP_F64
