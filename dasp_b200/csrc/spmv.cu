@@ -739,30 +739,30 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
                 }
             }
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
+        for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
 #pragma unroll
-    for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
-        const long tile = tile0 + j;
-        if (MODE == 1) {
-            A s = p[j] + __shfl_xor_sync(0xffffffffu, p[j], 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            long row = tile * 8 + r;
-            if (q == 0 && row < nrows) store_y<T>(a, a.y34 + row, s);
-        } else if (MODE == 0) {
-            A d1 = __shfl_down_sync(0xffffffffu, p[j], 1), d2 = __shfl_down_sync(0xffffffffu, p[j], 2);
-            long pair = tile * 8 + r;
-            if (pair < nrows) {
-                if (q == 0) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), p[j]);
-                if (q == 1) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), p[j] + d1 + d2);
-            }
-        } else {
-            A d1 = __shfl_down_sync(0xffffffffu, p[j], 1);
-            if ((q & 1) == 0) {
-                long yi = paired_y(a.G, tile, r, q >> 1);
-                if (yi < nrows) store_y<T>(a, a.y22 + yi, p[j] + d1);
+        for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
+            const long tile = tile0 + j;
+            if (MODE == 1) {
+                A s = p[j] + __shfl_xor_sync(0xffffffffu, p[j], 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                long row = tile * 8 + r;
+                if (q == 0 && row < nrows) store_y<T>(a, a.y34 + row, s);
+            } else if (MODE == 0) {
+                A d1 = __shfl_down_sync(0xffffffffu, p[j], 1), d2 = __shfl_down_sync(0xffffffffu, p[j], 2);
+                long pair = tile * 8 + r;
+                if (pair < nrows) {
+                    if (q == 0) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), p[j]);
+                    if (q == 1) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), p[j] + d1 + d2);
+                }
+            } else {
+                A d1 = __shfl_down_sync(0xffffffffu, p[j], 1);
+                if ((q & 1) == 0) {
+                    long yi = paired_y(a.G, tile, r, q >> 1);
+                    if (yi < nrows) store_y<T>(a, a.y22 + yi, p[j] + d1);
+                }
             }
         }
     }
