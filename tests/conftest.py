@@ -11,6 +11,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared libraries are build artefacts (git-ignored): build them when a fresh checkout runs the tests
+    import dasp_b200
+    from dasp_b200 import synth  # noqa: F401
+
+    if not (os.path.exists(dasp_b200.library_path())
+            and os.path.exists(os.path.join(os.path.dirname(dasp_b200.library_path()), "libdasp_synth.so"))):
+        dasp_b200.build()
 
 
 @pytest.fixture(scope="session")
