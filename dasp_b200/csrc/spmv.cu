@@ -910,14 +910,14 @@ int launches_per_spmv(const dasp_handle *) { return 1; }
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
 {
-    static thread_local double *scratch[64] = {nullptr};
-    int dev = 0;
-    DASP_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return DASP_ERR_INVALID; }
-    if (!scratch[dev]) DASP_CUDA(cudaMalloc(&scratch[dev], sizeof(double) * RED_CTAS));
-    sumsq_partial<<<RED_CTAS, 256, 0, st>>>(d_v, (long)count, scratch[dev]);
-    sumsq_final<<<1, 256, 0, st>>>(scratch[dev], RED_CTAS, d_out);
-    DASP_CUDA(cudaGetLastError());
+    // per-call, stream-ordered scratch for the block partials: concurrent calls on different streams do not share it
+    double *scratch = nullptr;
+    DASP_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * RED_CTAS, st));
+    sumsq_partial<<<RED_CTAS, 256, 0, st>>>(d_v, (long)count, scratch);
+    sumsq_final<<<1, 256, 0, st>>>(scratch, RED_CTAS, d_out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) { set_error("dasp_sumsq: %s", cudaGetErrorString(e)); return DASP_ERR_CUDA; }
     return DASP_OK;
 }
 

@@ -118,3 +118,30 @@ def test_scale_copy_to(cuda_device, count, offset):
     for d in dests:
         assert bool(torch.equal(d[offset:offset + count], v * 0.5))
         assert bool((d[:offset] == -1.0).all()) and bool((d[offset + count:] == -1.0).all())
+
+
+def test_two_handles_on_two_streams_interleaved(cuda_device):
+    """Handles are independent: two matrices multiplied and reduced on two streams at the same time."""
+    import torch
+
+    import dasp_b200
+
+    cases_ = [get("powerlaw_20k"), get("mixed_f1")]
+    hs = [dasp_b200.Dasp(dasp_b200.DASP_F64, m, n, rp, ci, v) for (m, n, rp, ci, v) in cases_]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    xs = [torch.from_numpy(x_for(c[1], seed=9 + i)).to(cuda_device) for i, c in enumerate(cases_)]
+    ys = [torch.zeros(c[0], dtype=torch.float64, device=cuda_device) for c in cases_]
+    n2 = [torch.zeros(1, dtype=torch.float64, device=cuda_device) for _ in cases_]
+    torch.cuda.synchronize()
+    for rep in range(20):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                hs[i].spmv_unpermuted(xs[i], ys[i], streams[i].cuda_stream)
+                dasp_b200.sumsq(ys[i], cases_[i][0], n2[i], streams[i].cuda_stream)
+    torch.cuda.synchronize()
+    for i, (m, n, rp, ci, v) in enumerate(cases_):
+        y_ref = oracle.csr_spmv_f64(m, rp, ci, v, xs[i].cpu().numpy())
+        assert np.linalg.norm(ys[i].cpu().numpy() - y_ref) <= 1e-12 * np.linalg.norm(y_ref)
+        assert abs(n2[i].item() - float(np.dot(y_ref, y_ref))) <= 1e-11 * float(np.dot(y_ref, y_ref))
+    for h in hs:
+        h.close()
