@@ -7,12 +7,11 @@
 // Pipeline (one stream, two host read-backs of a few scalars):
 //   classify_count -> scan -> classify_scatter      stable 7-way partition of row ids      (P1,P3)
 //   gather_len -> radix sort (stable, descending)   medium rows by length                  (P8)
+// The two generic primitives (exclusive scan, stable LSD radix sort) are hand-written below as well: no library call
+// is left on the path.
 //   block_fill / long_warps -> scans                blockPtr, irreg_rpt, long_rpt_new      (P11,P12)
 //   pack_short / pack_long / pack_irreg / pack_reg  padded value+index streams             (P6,P11,P13,P14)
 //   build_order                                     order_rid                              (P10)
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include "dasp_internal.h"
 
 namespace dasp {
@@ -396,14 +395,152 @@ __global__ void compress_long_cid(const int *__restrict__ unit_row, const int *_
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
-template <typename T>
-int scan_inplace(DevicePool &tmp_pool, T *d, int count, cudaStream_t st)
+// ---- exclusive prefix sum (in place, int32): tile sums -> recursive scan of the sums -> per-tile scan + offset ----
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int *__restrict__ d, int n, int *__restrict__ sums)
 {
-    size_t bytes = 0;
-    DASP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d, d, count, st));
-    void *tmp = nullptr;
-    DASP_TRY(tmp_pool.alloc(&tmp, bytes));
-    DASP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, d, d, count, st));
+    const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++)
+        if (base + j < n) t += d[base + j];
+    for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    __shared__ int w[SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; k++) tot += w[k];
+        sums[blockIdx.x] = tot;
+    }
+}
+
+// every thread owns SCAN_ITEMS consecutive entries (sequential order inside the tile), tile_offset = scanned tile sums
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply(int *__restrict__ d, int n, const int *__restrict__ tile_offset)
+{
+    const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], t = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        v[j] = base + j < n ? d[base + j] : 0;
+        t += v[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = t; // inclusive scan of the thread totals inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    __shared__ int w[SCAN_THREADS / 32];
+    if (lane == 31) w[warp] = incl;
+    __syncthreads();
+    int run = (tile_offset ? tile_offset[blockIdx.x] : 0) + incl - t;
+    for (int k = 0; k < warp; k++) run += w[k];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        if (base + j < n) d[base + j] = run;
+        run += v[j];
+    }
+}
+
+int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st)
+{
+    if (count <= 0) return DASP_OK;
+    const int tiles = (count + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles == 1) {
+        scan_tile_apply<<<1, SCAN_THREADS, 0, st>>>(d, count, nullptr);
+        return DASP_OK;
+    }
+    int *sums = nullptr;
+    DASP_TRY(tmp_pool.alloc((void **)&sums, sizeof(int) * (size_t)tiles));
+    scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(d, count, sums);
+    DASP_TRY(scan_inplace(tmp_pool, sums, tiles, st));
+    scan_tile_apply<<<tiles, SCAN_THREADS, 0, st>>>(d, count, sums);
+    return DASP_OK;
+}
+
+// ---- stable DESCENDING LSD radix sort of (key, value) pairs, 8 bits per pass (P8) ----
+// Same scheme as the category partition above: per-tile digit histogram (digit-major), one exclusive scan, stable
+// scatter with in-warp ranks from __match_any_sync.  Descending order = ascending order of (255 - digit).
+constexpr int RS_BINS = 256;
+static_assert(RS_BINS == TILE_THREADS, "one thread per digit bin");
+
+__device__ __forceinline__ int rs_digit(int key, int shift) { return 255 - ((key >> shift) & 255); }
+
+__global__ void __launch_bounds__(TILE_THREADS) radix_count(const int *__restrict__ keys, int n, int shift, int ntiles,
+                                                            int *__restrict__ counts)
+{
+    __shared__ int cnt[RS_BINS];
+    cnt[threadIdx.x] = 0; // TILE_THREADS == RS_BINS
+    __syncthreads();
+    const long base = (long)blockIdx.x * TILE_ROWS;
+    for (int p = 0; p < TILE_PASSES; p++) {
+        long i = base + p * TILE_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&cnt[rs_digit(keys[i], shift)], 1);
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) radix_scatter(const int *__restrict__ keys_in, const int *__restrict__ vals_in, int n,
+                                                              int shift, int ntiles, const int *__restrict__ offsets,
+                                                              int *__restrict__ keys_out, int *__restrict__ vals_out)
+{
+    constexpr int NW = TILE_THREADS / 32;
+    __shared__ int base[RS_BINS];
+    __shared__ int wcnt[NW][RS_BINS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    base[threadIdx.x] = offsets[(size_t)threadIdx.x * ntiles + blockIdx.x];
+    const long row0 = (long)blockIdx.x * TILE_ROWS;
+    for (int p = 0; p < TILE_PASSES; p++) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) wcnt[k][threadIdx.x] = 0;
+        __syncthreads();
+        const long i = row0 + p * TILE_THREADS + threadIdx.x;
+        const bool live = i < n;
+        const int key = live ? keys_in[i] : 0, val = live ? vals_in[i] : 0;
+        const int dg = live ? rs_digit(key, shift) : RS_BINS; // RS_BINS = "no element"
+        const unsigned same = __match_any_sync(0xffffffffu, dg);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        if (live && rank == 0) wcnt[warp][dg] = __popc(same);
+        __syncthreads();
+        if (live) {
+            int pos = base[dg] + rank;
+            for (int k = 0; k < warp; k++) pos += wcnt[k][dg];
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+        __syncthreads();
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) t += wcnt[k][threadIdx.x];
+        base[threadIdx.x] += t;
+        __syncthreads();
+    }
+}
+
+// sorts `n` pairs by the low `bits` bits of the key, descending and stable; the result is in keys_out / vals_out
+int radix_sort_desc(DevicePool &tmp, const int *keys_in, const int *vals_in, int *keys_out, int *vals_out, int n, int bits,
+                    cudaStream_t st)
+{
+    const int ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+    const int passes = (bits + 7) / 8;
+    int *counts = nullptr, *kbuf = nullptr, *vbuf = nullptr;
+    DASP_TRY(tmp.alloc((void **)&counts, sizeof(int) * ((size_t)RS_BINS * ntiles + 1)));
+    if (passes > 1) {
+        DASP_TRY(tmp.alloc((void **)&kbuf, sizeof(int) * (size_t)n));
+        DASP_TRY(tmp.alloc((void **)&vbuf, sizeof(int) * (size_t)n));
+    }
+    const int *ki = keys_in, *vi = vals_in;
+    for (int p = 0; p < passes; p++) {
+        // ping-pong so that the LAST pass lands in keys_out / vals_out
+        int *ko = ((passes - 1 - p) & 1) ? kbuf : keys_out, *vo = ((passes - 1 - p) & 1) ? vbuf : vals_out;
+        radix_count<<<ntiles, TILE_THREADS, 0, st>>>(ki, n, 8 * p, ntiles, counts);
+        DASP_TRY(scan_inplace(tmp, counts, RS_BINS * ntiles, st));
+        radix_scatter<<<ntiles, TILE_THREADS, 0, st>>>(ki, vi, n, 8 * p, ntiles, counts, ko, vo);
+        ki = ko; vi = vo;
+    }
     return DASP_OK;
 }
 
@@ -476,13 +613,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         gather_len<<<grid_for(cm, 256), 256, 0, st>>>(rowptr, cat_rid + seg[CAT_MED], cm, len_in);
         int end_bit = 1;
         while (end_bit < 31 && (1 << end_bit) < block_longest) end_bit++;
-        size_t bytes = 0;
-        DASP_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, len_in, ml, cat_rid + seg[CAT_MED], ms, cm, 0,
-                                                            end_bit, st));
-        void *sort_tmp = nullptr;
-        DASP_TRY(tmp.alloc(&sort_tmp, bytes));
-        DASP_CUDA(cub::DeviceRadixSort::SortPairsDescending(sort_tmp, bytes, len_in, ml, cat_rid + seg[CAT_MED], ms, cm, 0,
-                                                            end_bit, st));
+        DASP_TRY(radix_sort_desc(tmp, len_in, cat_rid + seg[CAT_MED], ml, ms, cm, end_bit, st));
     }
 
     // ---- P12: block fill analysis -> blockPtr, irreg_rpt ; P11: long_rpt_new ----
