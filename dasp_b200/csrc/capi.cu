@@ -100,7 +100,11 @@ int dasp_create(dasp_handle **out, dasp_dtype dtype, int device, int m, int n, i
         return DASP_ERR_INVALID;
     }
     if (nnz > INT32_MAX) { set_error("nnz=%lld does not fit the reference's 32-bit row pointers", (long long)nnz); return DASP_ERR_RANGE; }
-    DASP_CUDA(cudaSetDevice(device));
+    DASP_ON_DEVICE(device); // the caller's current device is restored on return
+    // Device-resident CSR arrays may still be being written by work the caller queued on other streams; the
+    // preprocessing runs on the handle's private non-blocking stream, which is not ordered against them.  dasp_create
+    // is a one-time, synchronous analyse step: wait for the device once instead of asking for a stream.
+    if (is_device_ptr(rowptr) || (nnz > 0 && (is_device_ptr(colidx) || is_device_ptr(val)))) DASP_CUDA(cudaDeviceSynchronize());
     dasp_handle *h = new (std::nothrow) dasp_handle();
     if (!h) { set_error("out of host memory"); return DASP_ERR_ALLOC; }
     h->device = device; h->dtype = dtype; h->threshold = threshold; h->block_longest = block_longest;
@@ -142,7 +146,7 @@ int dasp_create(dasp_handle **out, dasp_dtype dtype, int device, int m, int n, i
 int dasp_destroy(dasp_handle *h)
 {
     if (!h) return DASP_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     h->pool.free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (int k = 0; k < 3; k++) {
@@ -157,12 +161,14 @@ int dasp_destroy(dasp_handle *h)
 int dasp_spmv(dasp_handle *h, const void *d_x, void *d_y, void *stream)
 {
     if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv: NULL argument"); return DASP_ERR_INVALID; }
+    DASP_ON_DEVICE(h->device);
     return launch_spmv(h, d_x, d_y, nullptr, (cudaStream_t)stream);
 }
 
 int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *stream)
 {
     if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_unpermuted: NULL argument"); return DASP_ERR_INVALID; }
+    DASP_ON_DEVICE(h->device);
     return launch_spmv(h, d_x, d_y, h->L.order_rid, (cudaStream_t)stream);
 }
 
@@ -170,6 +176,7 @@ int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, 
 {
     if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_axpby: NULL argument"); return DASP_ERR_INVALID; }
     const double ab[2] = {alpha, beta};
+    DASP_ON_DEVICE(h->device);
     return launch_spmv(h, d_x, d_y, permuted ? nullptr : h->L.order_rid, (cudaStream_t)stream, ab);
 }
 
@@ -188,6 +195,7 @@ int dasp_spmv_scatter_to(dasp_handle *h, const void *d_x, void *const *d_dests, 
     m.n_extra = n_dests - 1;
     m.row_offset = row_offset;
     m.norm2 = d_norm2;
+    DASP_ON_DEVICE(h->device);
     return launch_spmv(h, d_x, d_dests[0], h->L.order_rid, (cudaStream_t)stream, nullptr, &m);
 }
 
@@ -206,22 +214,26 @@ int dasp_unpermute_to(dasp_handle *h, const void *d_y_perm, void *const *d_dests
     m.n_extra = n_dests - 1;
     m.row_offset = row_offset;
     m.norm2 = d_norm2;
+    DASP_ON_DEVICE(h->device);
     return unpermute_to(h, d_y_perm, m, d_dests[0], (cudaStream_t)stream);
 }
 
 // ---- checkpoint of the preprocessed layout ---------------------------------------------------------
+// The file holds the reference layout only (the 12 bit-exact arrays + the scalars); everything else the kernels read is
+// re-derived on the GPU by derive() after loading, from arrays that were range-checked first.
 namespace {
-constexpr uint64_t kMagic = 0x3130305f50534144ull; // "DASP_001"
+constexpr uint64_t kMagic = 0x3230305f50534144ull; // "DASP_002"
+constexpr int32_t kFormatVersion = 2;
+constexpr int kFileArrays = 12;
 struct ArrayRef { void **ptr; int64_t bytes; };
 
-// every device array of the layout with its size, in file order
-int layout_arrays(dasp_handle *h, ArrayRef (&out)[24])
+// the reference arrays of the layout with their sizes, in file order
+void layout_arrays(dasp_handle *h, ArrayRef (&out)[kFileArrays])
 {
     Layout &L = h->L;
     const dasp_stats_t &s = L.s;
     const int64_t ev = (int64_t)L.esz, ei = sizeof(int);
-    const int64_t ngroups = ((int64_t)s.row_block + 31) / 32;
-    ArrayRef a[24] = {
+    const ArrayRef a[kFileArrays] = {
         {(void **)&L.order_rid, ei * s.m},
         {(void **)&L.long_rpt_new, ei * ((int64_t)s.row_long + 1)},
         {&L.long_val, ev * s.fill0_nnz_long},
@@ -234,43 +246,60 @@ int layout_arrays(dasp_handle *h, ArrayRef (&out)[24])
         {(void **)&L.reg_cid, ei * s.fill0_nnz_reg},
         {&L.short_val, ev * s.fill0_nnz_short},
         {(void **)&L.short_cid, ei * s.fill0_nnz_short},
-        {(void **)&L.long_unit_row, ei * (int64_t)L.n_long_units},
-        {(void **)&L.long_unit_chunk, ei * (int64_t)L.n_long_units},
-        {(void **)&L.long_unit_first, ei * ((int64_t)s.row_long + 1)},
-        {&L.long_partial, 8 * (int64_t)L.n_long_units},
-        {(void **)&L.long_done, (int64_t)sizeof(unsigned) * s.row_long},
-        {(void **)&L.med_has_irreg, ngroups},
-        {(void **)&L.reg_cbase, ei * (int64_t)(s.fill0_nnz_reg / 32)},
-        {(void **)&L.reg_cdelta, 2 * (int64_t)s.fill0_nnz_reg},
-        {(void **)&L.blk_wide, (int64_t)s.blocknum},
-        {(void **)&L.long_cbase, ei * (int64_t)(s.fill0_nnz_long / 32)},
-        {(void **)&L.long_cdelta, 2 * (int64_t)s.fill0_nnz_long},
-        {(void **)&L.long_wide, (int64_t)L.n_long_units},
     };
-    for (int i = 0; i < 24; i++) out[i] = a[i];
-    return 24;
+    for (int i = 0; i < kFileArrays; i++) out[i] = a[i];
+}
+
+// scalars of a file: every count non-negative and consistent with m, n, nnz and with each other
+bool stats_plausible(const dasp_stats_t &s, int dtype, int block_longest)
+{
+    const int f16 = dtype == DASP_F16;
+    const int64_t ints[] = {s.m, s.n, s.row_long, s.row_block, s.row_zero, s.short_row_1, s.short_row_3, s.short_row_2, s.short_row_4,
+                            s.common_13, s.short_row_34, s.blocknum, s.warp_number, s.fill0_nnz_long, s.fill0_nnz_reg, s.nnz_irreg,
+                            s.fill0_nnz_short, s.fill0_nnz_short13, s.fill0_nnz_short34, s.fill0_nnz_short22, s.nnz_short,
+                            s.nnz_long, s.fill0_nnz_irreg, s.origin_nnz_reg};
+    for (int64_t v : ints)
+        if (v < 0) return false;
+    if (s.dtype != dtype || s.nnz < 0 || s.nnz > INT32_MAX || block_longest < 1) return false;
+    if (s.rowloop != 1 && s.rowloop != 2 && s.rowloop != 4) return false;
+    const int64_t rows = (int64_t)s.row_long + s.row_block + s.short_row_1 + 2 * (int64_t)s.common_13 + s.short_row_34 +
+                         s.short_row_2 + s.row_zero;
+    if (rows != s.m || s.short_row_34 != s.short_row_3 + s.short_row_4) return false;
+    if ((int64_t)s.nnz_long + s.nnz_short + s.origin_nnz_reg + s.nnz_irreg != s.nnz) return false; // src/dasp_f64.h:1091
+    if (s.blocknum % (4 * s.rowloop) || (int64_t)s.blocknum * 8 < s.row_block) return false;
+    if (s.warp_number % 4 || (int64_t)s.warp_number * (f16 ? 256 : 64) != s.fill0_nnz_long) return false;
+    if (s.fill0_nnz_reg % 32 || s.fill0_nnz_irreg != (f16 ? 2 * ((s.nnz_irreg + 1) / 2) : s.nnz_irreg)) return false;
+    const int64_t singles = f16 ? 2 * (((int64_t)s.short_row_1 + 1) / 2) : s.short_row_1;
+    if (singles + s.fill0_nnz_short13 + s.fill0_nnz_short34 + s.fill0_nnz_short22 != s.fill0_nnz_short) return false;
+    if (s.fill0_nnz_short13 % 32 || s.fill0_nnz_short34 % 32 || s.fill0_nnz_short22 % 32) return false;
+    if ((int64_t)s.fill0_nnz_short13 < 4 * (int64_t)s.common_13 || (int64_t)s.fill0_nnz_short34 < 4 * (int64_t)s.short_row_34 ||
+        (int64_t)s.fill0_nnz_short22 < 2 * (int64_t)s.short_row_2)
+        return false;
+    return true;
 }
 } // namespace
 
 int dasp_save(const dasp_handle *h, const char *path)
 {
     if (!h || !path) { set_error("dasp_save: NULL argument"); return DASP_ERR_INVALID; }
-    DASP_CUDA(cudaSetDevice(h->device));
+    DASP_ON_DEVICE(h->device);
     FILE *f = fopen(path, "wb");
     if (!f) { set_error("dasp_save: cannot open %s", path); return DASP_ERR_INVALID; }
-    ArrayRef arr[24];
-    const int n = layout_arrays(const_cast<dasp_handle *>(h), arr);
-    const int32_t head[4] = {(int32_t)h->dtype, h->block_longest, h->L.n_long_units, n};
+    ArrayRef arr[kFileArrays];
+    layout_arrays(const_cast<dasp_handle *>(h), arr);
+    const int32_t head[6] = {(int32_t)h->dtype, h->block_longest, kFileArrays, (int32_t)sizeof(dasp_stats_t), kFormatVersion, 0};
     bool ok = fwrite(&kMagic, 8, 1, f) == 1 && fwrite(head, sizeof(head), 1, f) == 1 && fwrite(&h->threshold, 8, 1, f) == 1 &&
               fwrite(&h->L.s, sizeof(dasp_stats_t), 1, f) == 1;
     std::vector<char> buf;
-    for (int i = 0; ok && i < n; i++) {
-        ok = fwrite(&arr[i].bytes, 8, 1, f) == 1;
-        if (!ok || arr[i].bytes == 0) continue;
-        buf.resize((size_t)arr[i].bytes);
-        if (cudaMemcpy(buf.data(), *arr[i].ptr, buf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
-        ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-    }
+    try {
+        for (int i = 0; ok && i < kFileArrays; i++) {
+            ok = fwrite(&arr[i].bytes, 8, 1, f) == 1;
+            if (!ok || arr[i].bytes == 0) continue;
+            buf.resize((size_t)arr[i].bytes);
+            if (cudaMemcpy(buf.data(), *arr[i].ptr, buf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+            ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+        }
+    } catch (const std::bad_alloc &) { ok = false; }
     ok = (fclose(f) == 0) && ok;
     if (!ok) { set_error("dasp_save: write to %s failed", path); return DASP_ERR_INVALID; }
     return DASP_OK;
@@ -282,35 +311,46 @@ int dasp_load(dasp_handle **out, const char *path, int device)
     *out = nullptr;
     FILE *f = fopen(path, "rb");
     if (!f) { set_error("dasp_load: cannot open %s", path); return DASP_ERR_INVALID; }
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{f};
     uint64_t magic = 0;
-    int32_t head[4] = {0, 0, 0, 0};
+    int32_t head[6] = {0, 0, 0, 0, 0, 0};
     double threshold = 0;
     dasp_stats_t st;
-    bool ok = fread(&magic, 8, 1, f) == 1 && magic == kMagic && fread(head, sizeof(head), 1, f) == 1 &&
-              fread(&threshold, 8, 1, f) == 1 && fread(&st, sizeof(st), 1, f) == 1 && head[3] == 24 &&
-              (head[0] == DASP_F64 || head[0] == DASP_F16);
-    if (!ok) { fclose(f); set_error("dasp_load: %s is not a DASP layout file", path); return DASP_ERR_INVALID; }
-    if (cudaSetDevice(device) != cudaSuccess) { fclose(f); set_error("dasp_load: cudaSetDevice(%d): %s", device, cudaGetErrorString(cudaGetLastError())); return DASP_ERR_CUDA; }
+    const bool ok = fread(&magic, 8, 1, f) == 1 && magic == kMagic && fread(head, sizeof(head), 1, f) == 1 &&
+                    head[2] == kFileArrays && head[3] == (int32_t)sizeof(dasp_stats_t) && head[4] == kFormatVersion &&
+                    fread(&threshold, 8, 1, f) == 1 && fread(&st, sizeof(st), 1, f) == 1 &&
+                    (head[0] == DASP_F64 || head[0] == DASP_F16);
+    if (!ok) { set_error("dasp_load: %s is not a DASP layout file of format %d", path, kFormatVersion); return DASP_ERR_INVALID; }
+    if (!(threshold > 0.0) || !stats_plausible(st, head[0], head[1])) {
+        set_error("dasp_load: %s: inconsistent layout scalars", path);
+        return DASP_ERR_INVALID;
+    }
+    DASP_ON_DEVICE(device);
     dasp_handle *h = new (std::nothrow) dasp_handle();
-    if (!h) { fclose(f); set_error("out of host memory"); return DASP_ERR_ALLOC; }
+    if (!h) { set_error("out of host memory"); return DASP_ERR_ALLOC; }
     h->device = device; h->dtype = (dasp_dtype)head[0]; h->block_longest = head[1]; h->threshold = threshold;
-    h->L.s = st; h->L.esz = head[0] == DASP_F16 ? 2 : 8; h->L.n_long_units = head[2];
+    h->L.s = st; h->L.esz = head[0] == DASP_F16 ? 2 : 8;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess ? DASP_OK : DASP_ERR_CUDA;
-    ArrayRef arr[24];
-    const int n = layout_arrays(h, arr);
+    ArrayRef arr[kFileArrays];
+    layout_arrays(h, arr);
     std::vector<char> buf;
-    for (int i = 0; rc == DASP_OK && i < n; i++) {
-        int64_t bytes = -1;
-        if (fread(&bytes, 8, 1, f) != 1 || bytes != arr[i].bytes) { set_error("dasp_load: %s is truncated or inconsistent", path); rc = DASP_ERR_INVALID; break; }
-        if ((rc = h->pool.alloc(arr[i].ptr, (size_t)bytes)) != DASP_OK) break;
-        if (bytes == 0) continue;
-        buf.resize((size_t)bytes);
-        if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { set_error("dasp_load: %s is truncated", path); rc = DASP_ERR_INVALID; break; }
-        if (cudaMemcpy(*arr[i].ptr, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("dasp_load: upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DASP_ERR_CUDA; }
-    }
-    fclose(f);
-    if (rc == DASP_OK && h->L.s.row_long > 0) cudaMemset(h->L.long_done, 0, sizeof(unsigned) * (size_t)h->L.s.row_long);
+    try {
+        for (int i = 0; rc == DASP_OK && i < kFileArrays; i++) {
+            int64_t bytes = -1;
+            if (fread(&bytes, 8, 1, f) != 1 || bytes != arr[i].bytes) { set_error("dasp_load: %s is truncated or inconsistent", path); rc = DASP_ERR_INVALID; break; }
+            if ((rc = h->pool.alloc(arr[i].ptr, (size_t)bytes)) != DASP_OK) break;
+            if (bytes == 0) continue;
+            buf.resize((size_t)bytes);
+            if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { set_error("dasp_load: %s is truncated", path); rc = DASP_ERR_INVALID; break; }
+            if (cudaMemcpy(*arr[i].ptr, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("dasp_load: upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DASP_ERR_CUDA; }
+        }
+    } catch (const std::bad_alloc &) { set_error("dasp_load: out of host memory"); rc = DASP_ERR_ALLOC; }
+    char extra;
+    if (rc == DASP_OK && fread(&extra, 1, 1, f) == 1) { set_error("dasp_load: %s has trailing data", path); rc = DASP_ERR_INVALID; }
+    // the offsets and indices the kernels will follow: checked on the device before anything is derived from them
+    if (rc == DASP_OK) rc = validate_layout(h, h->own_stream);
+    if (rc == DASP_OK) rc = derive(h, h->own_stream);
     if (rc != DASP_OK) { dasp_destroy(h); return rc; }
     h->L.s.device_bytes = h->pool.bytes;
     *out = h;
@@ -321,6 +361,7 @@ int dasp_spmv_timed(dasp_handle *h, const void *d_x, void *d_y, void *stream, in
 {
     if (!h || !total_ms || reps < 1 || warmup < 0) { set_error("dasp_spmv_timed: bad argument"); return DASP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    DASP_ON_DEVICE(h->device);
     for (int i = 0; i < warmup; i++) DASP_TRY(launch_spmv(h, d_x, d_y, nullptr, st));
     cudaEvent_t e0, e1;
     DASP_CUDA(cudaEventCreate(&e0));
@@ -340,15 +381,22 @@ int dasp_spmv_timed(dasp_handle *h, const void *d_x, void *d_y, void *stream, in
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host)
 {
     if (!h || (!x_host && h->L.s.n > 0) || (!y_host && h->L.s.m > 0)) { set_error("dasp_spmv_host: NULL argument"); return DASP_ERR_INVALID; }
-    DASP_CUDA(cudaSetDevice(h->device));
+    DASP_ON_DEVICE(h->device);
     const size_t esz = h->dtype == DASP_F16 ? 2 : 8;
     const size_t xb = esz * (size_t)h->L.s.n, yb = esz * (size_t)h->L.s.m;
-    if (!h->dx_stage) { // device-side staging buffers, allocated once
-        DASP_TRY(h->pool.alloc(&h->dx_stage, xb));
-        DASP_TRY(h->pool.alloc(&h->dy_stage, yb));
+    if (!h->dx_stage) { // device-side staging buffers, allocated once; committed only when both exist
+        void *dx = nullptr, *dy = nullptr;
+        DASP_TRY(h->pool.alloc(&dx, xb));
+        int rc = h->pool.alloc(&dy, yb);
+        if (rc != DASP_OK) { h->pool.release(dx); return rc; }
+        h->dx_stage = dx; h->dy_stage = dy;
     }
     cudaStream_t st = h->own_stream;
-    DASP_CUDA(cudaMemcpyAsync(h->dx_stage, x_host, xb, cudaMemcpyHostToDevice, st));
+    // only the columns that occur in the matrix are read by the product: upload x[col_min .. col_max] (a row slab of a
+    // banded / stencil matrix touches 1/P of x plus a halo)
+    const size_t xoff = esz * (size_t)h->L.s.col_min;
+    const size_t xlen = h->L.s.col_max >= h->L.s.col_min ? esz * ((size_t)h->L.s.col_max - h->L.s.col_min + 1) : 0;
+    if (xlen) DASP_CUDA(cudaMemcpyAsync((char *)h->dx_stage + xoff, (const char *)x_host + xoff, xlen, cudaMemcpyHostToDevice, st));
     DASP_TRY(launch_spmv(h, h->dx_stage, h->dy_stage, nullptr, st));
     DASP_CUDA(cudaMemcpyAsync(y_host, h->dy_stage, yb, cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaStreamSynchronize(st));
@@ -359,17 +407,22 @@ int dasp_spmv_host_batch(dasp_handle *h, const void *const *x_hosts, void *const
 {
     if (!h || count < 0 || (count > 0 && (!x_hosts || !y_hosts))) { set_error("dasp_spmv_host_batch: bad argument"); return DASP_ERR_INVALID; }
     if (count == 0) return DASP_OK;
-    DASP_CUDA(cudaSetDevice(h->device));
+    DASP_ON_DEVICE(h->device);
     const size_t esz = h->dtype == DASP_F16 ? 2 : 8;
     const size_t xb = esz * (size_t)h->L.s.n, yb = esz * (size_t)h->L.s.m;
-    if (!h->batch_stream[0]) {
-        for (int k = 0; k < 3; k++) DASP_CUDA(cudaStreamCreateWithFlags(&h->batch_stream[k], cudaStreamNonBlocking));
+    const size_t xoff = esz * (size_t)h->L.s.col_min; // only the column range of the matrix is uploaded (see dasp_spmv_host)
+    const size_t xlen = h->L.s.col_max >= h->L.s.col_min ? esz * ((size_t)h->L.s.col_max - h->L.s.col_min + 1) : 0;
+    if (!h->batch_ready) { // streams, events and staging are committed only when all of them exist
         for (int k = 0; k < 3; k++)
-            for (int b = 0; b < 2; b++) DASP_CUDA(cudaEventCreateWithFlags(&h->batch_ev[k][b], cudaEventDisableTiming));
+            if (!h->batch_stream[k]) DASP_CUDA(cudaStreamCreateWithFlags(&h->batch_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; k++)
+            for (int b = 0; b < 2; b++)
+                if (!h->batch_ev[k][b]) DASP_CUDA(cudaEventCreateWithFlags(&h->batch_ev[k][b], cudaEventDisableTiming));
         for (int b = 0; b < 2; b++) {
-            DASP_TRY(h->pool.alloc(&h->batch_dx[b], xb));
-            DASP_TRY(h->pool.alloc(&h->batch_dy[b], yb));
+            if (!h->batch_dx[b]) DASP_TRY(h->pool.alloc(&h->batch_dx[b], xb));
+            if (!h->batch_dy[b]) DASP_TRY(h->pool.alloc(&h->batch_dy[b], yb));
         }
+        h->batch_ready = 1;
     }
     cudaStream_t up = h->batch_stream[0], comp = h->batch_stream[1], down = h->batch_stream[2];
     cudaEvent_t(&ev)[3][2] = h->batch_ev; // [0] upload done, [1] kernel done, [2] download done, per staging buffer
@@ -378,7 +431,7 @@ int dasp_spmv_host_batch(dasp_handle *h, const void *const *x_hosts, void *const
         if (!x_hosts[i] && xb) { set_error("dasp_spmv_host_batch: x_hosts[%d] is NULL", i); return DASP_ERR_INVALID; }
         if (!y_hosts[i] && yb) { set_error("dasp_spmv_host_batch: y_hosts[%d] is NULL", i); return DASP_ERR_INVALID; }
         if (i >= 2) DASP_CUDA(cudaStreamWaitEvent(up, ev[1][b], 0)); // x staging b free once product i-2 was multiplied
-        DASP_CUDA(cudaMemcpyAsync(h->batch_dx[b], x_hosts[i], xb, cudaMemcpyHostToDevice, up));
+        if (xlen) DASP_CUDA(cudaMemcpyAsync((char *)h->batch_dx[b] + xoff, (const char *)x_hosts[i] + xoff, xlen, cudaMemcpyHostToDevice, up));
         DASP_CUDA(cudaEventRecord(ev[0][b], up));
         DASP_CUDA(cudaStreamWaitEvent(comp, ev[0][b], 0));
         if (i >= 2) DASP_CUDA(cudaStreamWaitEvent(comp, ev[2][b], 0)); // y staging b free once product i-2 was downloaded
@@ -456,7 +509,7 @@ int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t 
         if (bytes) *bytes = e.bytes;
         if (!host_dst) return DASP_OK;
         if (cap_bytes < e.bytes) { set_error("dasp_export(%s): need %lld bytes, got %lld", name, (long long)e.bytes, (long long)cap_bytes); return DASP_ERR_BUFFER; }
-        DASP_CUDA(cudaSetDevice(h->device));
+        DASP_ON_DEVICE(h->device);
         if (e.bytes > 0) DASP_CUDA(cudaMemcpy(host_dst, e.ptr, (size_t)e.bytes, cudaMemcpyDeviceToHost));
         return DASP_OK;
     }
@@ -468,6 +521,10 @@ int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows
 {
     if (!h) { set_error("dasp_set_variant: NULL handle"); return DASP_ERR_INVALID; }
     h->var_medium = medium; h->var_long = long_rows; h->var_short = short_rows;
+    if (long_rows == DASP_VARIANT_BLOCKED && !h->L.lcb_val) { // build the column-blocked copy on demand
+        DASP_ON_DEVICE(h->device);
+        DASP_TRY(build_lcb(h, h->own_stream));
+    }
     return DASP_OK;
 }
 

@@ -28,6 +28,32 @@ void set_error(const char *fmt, ...);
         if (s_ != DASP_OK) return s_;    \
     } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards (one handle per GPU
+// in one process: every entry that touches a handle's memory or launches on it goes through this).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        status = cudaGetDevice(&prev);
+        if (status == cudaSuccess && prev != device) {
+            status = cudaSetDevice(device);
+            switched = status == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define DASP_ON_DEVICE(dev)                                                                       \
+    ::dasp::DeviceGuard device_guard_(dev);                                                       \
+    if (device_guard_.status != cudaSuccess) {                                                    \
+        ::dasp::set_error("cannot select device %d: %s", (dev), cudaGetErrorString(device_guard_.status)); \
+        cudaGetLastError();                                                                       \
+        return DASP_ERR_CUDA;                                                                     \
+    }
+
 // Tracks every device allocation of a handle so destroy/fail paths free them all.
 struct DevicePool {
     std::vector<void *> ptrs;
@@ -75,14 +101,31 @@ struct Layout {
     int *long_cbase = nullptr;              // [fill0_nnz_long / 32] same compact form for the long part
     unsigned short *long_cdelta = nullptr;  // [fill0_nnz_long]
     unsigned char *long_wide = nullptr;     // [n_long_units] in execution order
-    int *inv_order = nullptr;               // [m] inverse of order_rid, built on first use by dasp_unpermute_to
+    int *inv_order = nullptr;               // [m] inverse of order_rid (original row -> permuted index)
     unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
+    double long_lines_avg = 0.0;            // estimated distinct 128-byte lines of x per 32-slot group of the long part
+    // Column-blocked copy of the long part ("LCB", built when the long rows gather x all over the place): the live
+    // entries of all long rows sorted by (column block, long row); a CTA stages one block of x in shared memory with a
+    // TMA bulk copy and gathers from there.  12 (f64) / 6 (f16) bytes per entry like the CSR itself.
+    int lcb_bw_log2 = 0;                    // block width = 1 << lcb_bw_log2 columns
+    int lcb_nblk = 0;                       // column blocks
+    int lcb_live = 0;                       // entries (padding dropped)
+    int lcb_nctas = 0;                      // CTAs of the LCB kernel (LCB_PART entries each, never across blocks)
+    void *lcb_val = nullptr;                // [lcb_live]
+    unsigned short *lcb_col = nullptr;      // [lcb_live] column - block * width
+    unsigned short *lcb_row = nullptr;      // [lcb_live] long-row index (row_long <= 65535)
+    int *lcb_blk_ptr = nullptr;             // [lcb_nblk + 1] first entry of each block
+    int *lcb_cta_first = nullptr;           // [lcb_nblk + 1] first CTA of each block
+    void *lcb_acc = nullptr;                // [row_long] accumulators (double / float), zero between launches
+    unsigned *lcb_done = nullptr;           // [1] CTAs finished in the current launch (self-resetting)
 };
 
 } // namespace dasp
 
 struct dasp_handle {
     int device = 0;
+    int lcb_attr_set = 0; // lcb_kernel dynamic shared memory attribute set on this device
+    int lcb_auto = 0; // AUTO uses the column-blocked long-row kernel (decided in derive() from long_lines_avg)
     dasp_dtype dtype = DASP_F64;
     double threshold = 0.75;
     int block_longest = 256;
@@ -97,13 +140,26 @@ struct dasp_handle {
     void *dx_stage = nullptr, *dy_stage = nullptr;
     cudaStream_t own_stream = nullptr;
     // dasp_spmv_host_batch: upload / compute / download streams, double-buffered staging and hand-over events
+    int batch_ready = 0;
     cudaStream_t batch_stream[3] = {nullptr, nullptr, nullptr};
     void *batch_dx[2] = {nullptr, nullptr}, *batch_dy[2] = {nullptr, nullptr};
     cudaEvent_t batch_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 namespace dasp {
+constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
+constexpr int LCB_PART = 16384;     // entries per CTA of the column-blocked long-row kernel
+constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
+
 // preprocess.cu
+int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st);
+int radix_sort_pairs(DevicePool &tmp, const int *keys_in, const int *vals_in, int *keys_out, int *vals_out, int n, int bits,
+                     bool descending, cudaStream_t st);
+// derive.cu: kernel-facing data derived from the reference layout (also after dasp_load); build_lcb on demand
+int derive(dasp_handle *h, cudaStream_t st);
+int build_lcb(dasp_handle *h, cudaStream_t st);
+// range / monotonicity check of the offset and index arrays of a layout read from a file (dasp_load)
+int validate_layout(dasp_handle *h, cudaStream_t st);
 int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx,
                const void *d_val, cudaStream_t st);
 // spmv.cu

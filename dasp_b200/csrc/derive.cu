@@ -1,0 +1,387 @@
+// derive.cu — everything the SpMV kernels read that is NOT part of the reference's layout, derived on the GPU from the
+// bit-exact arrays of preprocess.cu (or of a file read by dasp_load): long-row work units and their merge scratch,
+// compact 16-bit column indices, irregular-tail flags, the inverse permutation, and — for long rows whose gathers are
+// scattered over x — a column-blocked copy of the long part (LCB) whose kernel stages x in shared memory with TMA.
+#include <stdlib.h>
+
+#include "dasp_internal.h"
+
+namespace dasp {
+
+namespace {
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// work units per long row: one unit = LONG_UNIT_WARPS reference warps (src/dasp_f64.h:1006 defines the warp)
+__global__ void units_per_row(const int *__restrict__ long_rpt_new, int row_long, int *__restrict__ upr)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_long) return;
+    int w = long_rpt_new[i + 1] - long_rpt_new[i];
+    upr[i] = (w + LONG_UNIT_WARPS - 1) / LONG_UNIT_WARPS;
+}
+
+__global__ void __launch_bounds__(256) invert_order(const int *__restrict__ order, int m, int *__restrict__ inv)
+{
+    int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < m) inv[order[k]] = k;
+}
+
+// Execution order of the long-row work units.  Inside every group of 8 consecutive long rows the units are
+// enumerated chunk-major (chunk c of rows 8g..8g+7, then chunk c+1, ...), so the 8 warps of one CTA work on the
+// SAME slot range of 8 neighbouring long rows: rows that are long because they touch the same dense column range
+// (borders, constraints) then share their x sectors through that SM's L1.  Rows with fewer chunks simply drop out.
+__global__ void fill_long_units(const int *__restrict__ unit_first, int row_long, int *__restrict__ unit_row,
+                                int *__restrict__ unit_chunk)
+{
+    const int r0 = blockIdx.x * 8;
+    int n[8], base = unit_first[r0], most = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        n[r] = (r0 + r < row_long) ? unit_first[r0 + r + 1] - unit_first[r0 + r] : 0;
+        most = max(most, n[r]);
+    }
+    for (int c = threadIdx.x; c < most; c += blockDim.x) {
+        int pos = base;
+#pragma unroll
+        for (int r = 0; r < 8; r++) pos += min(n[r], c);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (n[r] > c) { unit_row[pos] = r0 + r; unit_chunk[pos] = c; pos++; }
+    }
+}
+
+// one flag per 32 sorted medium rows: does any of them own an irregular tail?
+__global__ void flag_irreg(const int *__restrict__ irreg_rpt, int row_block, int ngroups, unsigned char *__restrict__ flag)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    int hi = min(32 * (g + 1), row_block);
+    flag[g] = irreg_rpt[hi] != irreg_rpt[32 * g];
+}
+
+// Resident compact form of reg_cid: one warp per 8-row block walks its tiles; per tile the smallest non-zero
+// column is the base and every slot stores (column - base) in 16 bits.  Column 0 (all padding slots, and genuine
+// entries of column 0) is the sentinel 0xFFFF, so the kernels gather exactly the x entries the reference layout
+// names.  A block with a tile spanning >= 65535 columns is flagged wide and keeps using reg_cid.
+__global__ void compress_cid(const int *__restrict__ blockPtr, const int *__restrict__ reg_cid, int blocknum,
+                             int *__restrict__ cbase, unsigned short *__restrict__ cdelta, unsigned char *__restrict__ wide)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= blocknum) return;
+    const int lane = threadIdx.x & 31;
+    const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
+    bool any_wide = false;
+    for (int p = bp0; p < bp1; p += 32) {
+        const int c = reg_cid[p + lane];
+        int mn = c ? c : INT32_MAX, mx = c;
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == INT32_MAX) mn = 0; // tile of zeros only
+        const bool ok = (mx - mn) < 65535;
+        any_wide |= !ok;
+        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
+        if (lane == 0) cbase[p >> 5] = mn;
+    }
+    if (lane == 0) wide[b] = any_wide ? 1 : 0;
+}
+
+// The same compact index form for the long part: one warp per work unit (execution order), one base per 32-slot
+// group; a unit with a group spanning >= 65535 columns is flagged wide and keeps using long_cid.
+__global__ void compress_long_cid(const int *__restrict__ unit_row, const int *__restrict__ unit_chunk,
+                                  const int *__restrict__ long_rpt_new, const int *__restrict__ long_cid, int n_units,
+                                  int longw, int unit_warps, int esz, int *__restrict__ cbase, unsigned short *__restrict__ cdelta,
+                                  unsigned char *__restrict__ wide, unsigned long long *__restrict__ lines)
+{
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_units) return;
+    const int lane = threadIdx.x & 31;
+    const int row = unit_row[u];
+    const long row_end = (long)long_rpt_new[row + 1] * longw;
+    const long beg = (long)long_rpt_new[row] * longw + (long)unit_chunk[u] * unit_warps * longw;
+    const long end = min(beg + (long)unit_warps * longw, row_end);
+    bool any_wide = false;
+    unsigned long long nlines = 0;
+    for (long p = beg; p < end; p += 32) {
+        const int c = long_cid[p + lane];
+        int mn = c ? c : INT32_MAX, mx = c;
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == INT32_MAX) mn = 0;
+        // 128-byte lines of x one 32-lane gather of this group touches, estimated from its column span
+        nlines += (unsigned long long)min(32L, ((long)(mx - mn) * esz >> 7) + 1);
+        const bool ok = (mx - mn) < 65535;
+        any_wide |= !ok;
+        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
+        if (lane == 0) cbase[p >> 5] = mn;
+    }
+    if (lane == 0) wide[u] = any_wide ? 1 : 0;
+    if (lane == 0 && nlines) atomicAdd(lines, nlines);
+}
+
+
+// ---- LCB: column-blocked copy of the long part -----------------------------------------------------------------
+
+// long row of every reference warp (the reference's rid_by_warp, src/dasp_f64.h:1021-1031)
+__global__ void lcb_warp_rows(const int *__restrict__ long_rpt_new, int row_long, int *__restrict__ warp_row)
+{
+    const int i = blockIdx.x;
+    for (int w = long_rpt_new[i] + threadIdx.x; w < long_rpt_new[i + 1]; w += blockDim.x) warp_row[w] = i;
+}
+
+// sort key of every slot of the padded long part: its column block; padding (value 0 AND column 0) sorts last
+template <typename T>
+__global__ void lcb_keys(const T *__restrict__ long_val, const int *__restrict__ long_cid, int slots, int bw_log2, int nblk,
+                         int *__restrict__ key, int *__restrict__ idx)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= slots) return;
+    const int c = long_cid[p];
+    const bool live = !(c == 0 && long_val[p] == T(0));
+    key[p] = live ? (c >> bw_log2) : nblk;
+    idx[p] = p;
+}
+
+// first entry of every block in the sorted key sequence (lower bound), one thread per block
+__global__ void lcb_block_ptr(const int *__restrict__ sorted_key, int slots, int nblk, int *__restrict__ blk_ptr)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblk) return;
+    int lo = 0, hi = slots;
+    while (lo < hi) {
+        const int mid = (int)(((long)lo + hi) >> 1);
+        if (sorted_key[mid] < b) lo = mid + 1; else hi = mid;
+    }
+    blk_ptr[b] = lo;
+}
+
+__global__ void lcb_ctas_per_block(const int *__restrict__ blk_ptr, int nblk, int *__restrict__ cta_first)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblk) return;
+    cta_first[b] = b < nblk ? (blk_ptr[b + 1] - blk_ptr[b] + LCB_PART - 1) / LCB_PART : 0;
+}
+
+template <typename T>
+__global__ void lcb_gather(const T *__restrict__ long_val, const int *__restrict__ long_cid, const int *__restrict__ src,
+                           const int *__restrict__ warp_row, int live, int longw, int bw_mask, T *__restrict__ val,
+                           unsigned short *__restrict__ col, unsigned short *__restrict__ row)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= live) return;
+    const int p = src[i];
+    val[i] = long_val[p];
+    col[i] = (unsigned short)(long_cid[p] & bw_mask);
+    row[i] = (unsigned short)warp_row[p / longw];
+}
+
+template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    if (L.lcb_val || s.row_long == 0 || s.row_long > 65535 || s.fill0_nnz_long == 0) return DASP_OK;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    DevicePool &pool = h->pool;
+    const int slots = s.fill0_nnz_long, longw = sizeof(T) == 2 ? 256 : 64;
+    int bw_log2 = 0;
+    while ((sizeof(T) << (bw_log2 + 1)) <= (size_t)LCB_BYTES) bw_log2++; // 8192 doubles / 32768 halves
+    const int nblk = s.n > 0 ? (int)((((int64_t)s.n - 1) >> bw_log2) + 1) : 1;
+    int *warp_row = nullptr, *key = nullptr, *idx = nullptr, *skey = nullptr, *sidx = nullptr;
+    DASP_TRY(tmp.alloc((void **)&warp_row, sizeof(int) * (size_t)s.warp_number));
+    DASP_TRY(tmp.alloc((void **)&key, sizeof(int) * (size_t)slots));
+    DASP_TRY(tmp.alloc((void **)&idx, sizeof(int) * (size_t)slots));
+    DASP_TRY(tmp.alloc((void **)&skey, sizeof(int) * (size_t)slots));
+    DASP_TRY(tmp.alloc((void **)&sidx, sizeof(int) * (size_t)slots));
+    DASP_CUDA(cudaMemsetAsync(warp_row, 0, sizeof(int) * (size_t)s.warp_number, st));
+    lcb_warp_rows<<<s.row_long, 256, 0, st>>>(L.long_rpt_new, s.row_long, warp_row);
+    lcb_keys<T><<<grid_for(slots, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, slots, bw_log2, nblk, key, idx);
+    int bits = 1;
+    while ((1 << bits) <= nblk) bits++;
+    DASP_TRY(radix_sort_pairs(tmp, key, idx, skey, sidx, slots, bits, false, st));
+    DASP_TRY(pool.alloc((void **)&L.lcb_blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
+    DASP_TRY(pool.alloc((void **)&L.lcb_cta_first, sizeof(int) * (size_t)(nblk + 1)));
+    lcb_block_ptr<<<grid_for(nblk + 1, 256), 256, 0, st>>>(skey, slots, nblk, L.lcb_blk_ptr);
+    lcb_ctas_per_block<<<grid_for(nblk + 1, 256), 256, 0, st>>>(L.lcb_blk_ptr, nblk, L.lcb_cta_first);
+    DASP_TRY(scan_inplace(tmp, L.lcb_cta_first, nblk + 1, st));
+    int tot[2] = {0, 0};
+    DASP_CUDA(cudaMemcpyAsync(&tot[0], L.lcb_blk_ptr + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaMemcpyAsync(&tot[1], L.lcb_cta_first + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    const int live = tot[0];
+    DASP_TRY(pool.alloc(&L.lcb_val, sizeof(T) * (size_t)live));
+    DASP_TRY(pool.alloc((void **)&L.lcb_col, sizeof(unsigned short) * (size_t)live));
+    DASP_TRY(pool.alloc((void **)&L.lcb_row, sizeof(unsigned short) * (size_t)live));
+    DASP_TRY(pool.alloc(&L.lcb_acc, 8 * (size_t)s.row_long));
+    DASP_TRY(pool.alloc((void **)&L.lcb_done, sizeof(unsigned) * 4));
+    DASP_CUDA(cudaMemsetAsync(L.lcb_acc, 0, 8 * (size_t)s.row_long, st));
+    DASP_CUDA(cudaMemsetAsync(L.lcb_done, 0, sizeof(unsigned) * 4, st));
+    if (live > 0)
+        lcb_gather<T><<<grid_for(live, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, sidx, warp_row, live, longw,
+                                                          (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_col, L.lcb_row);
+    DASP_CUDA(cudaGetLastError());
+    DASP_CUDA(cudaStreamSynchronize(st)); // the scratch is released by the guard
+    L.lcb_bw_log2 = bw_log2; L.lcb_nblk = nblk; L.lcb_live = live; L.lcb_nctas = tot[1];
+    return DASP_OK;
+}
+
+// flag |= 1 unless a[0] == first, a non-decreasing and a[count-1] == last
+__global__ void check_offsets(const int *__restrict__ a, long count, int first, int last, int *__restrict__ flag)
+{
+    bool bad = false;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        const int v = a[i];
+        if (i == 0 && v != first) bad = true;
+        if (i == count - 1 ? v != last : v > a[i + 1]) bad = true;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+// flag |= 1 unless every a[i] lies in [0, hi)
+__global__ void check_range(const int *__restrict__ a, long count, int hi, int *__restrict__ flag)
+{
+    bool bad = false;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        const int v = a[i];
+        if (v < 0 || v >= hi) bad = true;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+// flag |= 1 unless a[0..count) is a permutation of 0..count-1 (seen: zeroed scratch of count ints)
+__global__ void check_permutation(const int *__restrict__ a, int count, int *__restrict__ seen, int *__restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int v = a[i];
+    if (v < 0 || v >= count || atomicExch(seen + v, 1) != 0) atomicOr(flag, 1);
+}
+
+} // namespace
+
+int validate_layout(dasp_handle *h, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    int *flag = nullptr, *seen = nullptr;
+    DASP_TRY(tmp.alloc((void **)&flag, sizeof(int)));
+    DASP_TRY(tmp.alloc((void **)&seen, sizeof(int) * (size_t)(s.m > 0 ? s.m : 1)));
+    DASP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    DASP_CUDA(cudaMemsetAsync(seen, 0, sizeof(int) * (size_t)(s.m > 0 ? s.m : 1), st));
+    const int G = 592;
+    const int longw = h->dtype == DASP_F16 ? 256 : 64;
+    check_offsets<<<G, 256, 0, st>>>(L.blockPtr, (long)s.blocknum + 1, 0, s.fill0_nnz_reg, flag);
+    check_offsets<<<G, 256, 0, st>>>(L.irreg_rpt, (long)s.row_block + 1, 0, s.nnz_irreg, flag);
+    if (s.row_long > 0) {
+        // long_rpt_new[row_long] = warps actually used, rounded up to warp_number by the reference (src/dasp_f64.h:1017)
+        int last = 0;
+        DASP_CUDA(cudaMemcpyAsync(&last, L.long_rpt_new + s.row_long, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DASP_CUDA(cudaStreamSynchronize(st));
+        if (last < 0 || last > s.warp_number || (int64_t)last * longw < s.nnz_long) { set_error("dasp_load: long_rpt_new does not match the layout scalars"); return DASP_ERR_INVALID; }
+        check_offsets<<<G, 256, 0, st>>>(L.long_rpt_new, (long)s.row_long + 1, 0, last, flag);
+    }
+    if (s.n > 0) {
+        check_range<<<G, 256, 0, st>>>(L.long_cid, s.fill0_nnz_long, s.n, flag);
+        check_range<<<G, 256, 0, st>>>(L.reg_cid, s.fill0_nnz_reg, s.n, flag);
+        check_range<<<G, 256, 0, st>>>(L.irreg_cid, s.nnz_irreg, s.n, flag);
+        check_range<<<G, 256, 0, st>>>(L.short_cid, s.fill0_nnz_short, s.n, flag);
+    } else if ((int64_t)s.fill0_nnz_long + s.fill0_nnz_reg + s.nnz_irreg + s.fill0_nnz_short > 0) {
+        set_error("dasp_load: entries in a matrix without columns");
+        return DASP_ERR_INVALID;
+    }
+    if (s.m > 0) check_permutation<<<grid_for(s.m, 256), 256, 0, st>>>(L.order_rid, s.m, seen, flag);
+    int bad = 0;
+    DASP_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    DASP_CUDA(cudaGetLastError());
+    if (bad) { set_error("dasp_load: offset / index arrays of the file are out of range or not monotone"); return DASP_ERR_INVALID; }
+    return DASP_OK;
+}
+
+int build_lcb(dasp_handle *h, cudaStream_t st)
+{
+    // T only needs the right size and an exact zero test: half bits as unsigned short (+0; -0 counts as live, harmless)
+    int rc = h->dtype == DASP_F16 ? build_lcb_t<unsigned short>(h, st) : build_lcb_t<double>(h, st);
+    h->L.s.device_bytes = h->pool.bytes;
+    return rc;
+}
+
+int derive(dasp_handle *h, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    DevicePool &pool = h->pool;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    const int cl = s.row_long, cm = s.row_block, blocknum = s.blocknum, m = s.m;
+    const int longw = h->dtype == DASP_F16 ? 256 : 64, esz = (int)L.esz;
+
+    // ---- long rows: work units (execution order), merge scratch, compact indices ----
+    DASP_TRY(pool.alloc((void **)&L.long_unit_first, sizeof(int) * (size_t)(cl + 1)));
+    DASP_CUDA(cudaMemsetAsync(L.long_unit_first, 0, sizeof(int) * (size_t)(cl + 1), st));
+    unsigned long long *lines = nullptr;
+    DASP_TRY(tmp.alloc((void **)&lines, sizeof(unsigned long long)));
+    DASP_CUDA(cudaMemsetAsync(lines, 0, sizeof(unsigned long long), st));
+    L.n_long_units = 0;
+    if (cl > 0) {
+        units_per_row<<<grid_for(cl, 256), 256, 0, st>>>(L.long_rpt_new, cl, L.long_unit_first);
+        DASP_TRY(scan_inplace(tmp, L.long_unit_first, cl + 1, st));
+        DASP_CUDA(cudaMemcpyAsync(&L.n_long_units, L.long_unit_first + cl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DASP_CUDA(cudaStreamSynchronize(st));
+    }
+    DASP_TRY(pool.alloc((void **)&L.long_unit_row, sizeof(int) * (size_t)L.n_long_units));
+    DASP_TRY(pool.alloc((void **)&L.long_unit_chunk, sizeof(int) * (size_t)L.n_long_units));
+    DASP_TRY(pool.alloc(&L.long_partial, 8 * (size_t)L.n_long_units));
+    DASP_TRY(pool.alloc((void **)&L.long_done, sizeof(unsigned) * (size_t)cl));
+    DASP_TRY(pool.alloc((void **)&L.long_cbase, sizeof(int) * (size_t)(s.fill0_nnz_long / 32)));
+    DASP_TRY(pool.alloc((void **)&L.long_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_long));
+    DASP_TRY(pool.alloc((void **)&L.long_wide, (size_t)L.n_long_units));
+    DASP_CUDA(cudaMemsetAsync(L.long_done, 0, sizeof(unsigned) * (size_t)cl, st));
+    if (cl > 0 && L.n_long_units > 0) {
+        fill_long_units<<<(cl + 7) / 8, 128, 0, st>>>(L.long_unit_first, cl, L.long_unit_row, L.long_unit_chunk);
+        compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(
+            L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.long_cid, L.n_long_units, longw, LONG_UNIT_WARPS, esz,
+            L.long_cbase, L.long_cdelta, L.long_wide, lines);
+    }
+    // ---- medium rows: irregular-tail flags, compact indices ----
+    const int ngroups = ceil_div(cm, 32);
+    DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
+    DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
+    DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
+    DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
+    if (cm > 0) flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
+    if (blocknum > 0)
+        compress_cid<<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(L.blockPtr, L.reg_cid, blocknum, L.reg_cbase,
+                                                                          L.reg_cdelta, L.blk_wide);
+    // ---- inverse permutation (dasp_unpermute_to, relabelled mode) ----
+    DASP_TRY(pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
+    if (m > 0) invert_order<<<grid_for(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
+    DASP_CUDA(cudaGetLastError());
+
+    // ---- scattered long rows: column-blocked copy.  Decision: average number of distinct 128-byte lines of x that one
+    // 32-lane gather of the chunked kernel touches (estimated from the column span of every 32-slot group) ----
+    L.long_lines_avg = 0.0;
+    h->lcb_auto = 0;
+    if (cl > 0 && s.fill0_nnz_long > 0) {
+        unsigned long long nl = 0;
+        DASP_CUDA(cudaMemcpyAsync(&nl, lines, sizeof(nl), cudaMemcpyDeviceToHost, st));
+        DASP_CUDA(cudaStreamSynchronize(st));
+        L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
+        double thr = 12.0; // measured crossover, profiles/r02/README.md
+        if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
+        if (L.long_lines_avg > thr && cl <= 65535 && s.nnz_long >= 4 * LCB_PART) {
+            DASP_TRY(build_lcb(h, st));
+            h->lcb_auto = L.lcb_nctas > 0;
+        }
+    }
+    DASP_CUDA(cudaStreamSynchronize(st));
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
+} // namespace dasp

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -95,8 +97,8 @@ extern "C" {
 
 void dasp_free_host(void *p) { free(p); }
 
-int dasp_read_mtx(const char *filename, dasp_dtype dtype, int *m, int *n, int64_t *nnz, int *is_symmetric, int **rowptr,
-                  int **colidx, void **val)
+static int read_mtx_impl(const char *filename, dasp_dtype dtype, int *m, int *n, int64_t *nnz, int *is_symmetric, int **rowptr,
+                         int **colidx, void **val)
 {
     if (!filename || !m || !n || !nnz || !rowptr || !colidx || !val || (dtype != DASP_F64 && dtype != DASP_F16)) {
         dasp::set_error("dasp_read_mtx: bad argument");
@@ -142,6 +144,12 @@ int dasp_read_mtx(const char *filename, dasp_dtype dtype, int *m, int *n, int64_
         dasp::set_error("%s: bad size line", filename);
         return DASP_ERR_INVALID;
     }
+    // the mirror of a symmetric / hermitian entry (i, j) is stored in row j: that row must exist (the reference writes
+    // out of bounds there, src/mmio_highlevel.h:722-745)
+    if (sym && M != N) { dasp::set_error("%s: symmetric matrix with %ld rows and %ld columns", filename, M, N); return DASP_ERR_INVALID; }
+    // every entry needs at least "i j" plus a separator: a size line that promises more entries than the file can hold is
+    // rejected before anything is allocated for it
+    if ((unsigned long)K > (unsigned long)(end - p) / 4 + 1) { dasp::set_error("%s: size line announces %ld entries, the file is too short for that", filename, K); return DASP_ERR_INVALID; }
     std::vector<int> ri((size_t)K), cj((size_t)K);
     std::vector<double> vv((size_t)K);
     for (long i = 0; i < K; i++) {
@@ -161,6 +169,21 @@ int dasp_read_mtx(const char *filename, dasp_dtype dtype, int *m, int *n, int64_
     if (is_symmetric) *is_symmetric = sym ? 1 : 0;
     if (dtype == DASP_F16) return build<unsigned short>(ri, cj, vv, (int)M, sym, nnz, rowptr, colidx, val);
     return build<double>(ri, cj, vv, (int)M, sym, nnz, rowptr, colidx, val);
+}
+
+// no exception crosses the C ABI: allocation failures of the parser become a status code
+int dasp_read_mtx(const char *filename, dasp_dtype dtype, int *m, int *n, int64_t *nnz, int *is_symmetric, int **rowptr,
+                  int **colidx, void **val)
+{
+    try {
+        return read_mtx_impl(filename, dtype, m, n, nnz, is_symmetric, rowptr, colidx, val);
+    } catch (const std::bad_alloc &) {
+        dasp::set_error("dasp_read_mtx: out of host memory");
+        return DASP_ERR_ALLOC;
+    } catch (const std::exception &e) {
+        dasp::set_error("dasp_read_mtx: %s", e.what());
+        return DASP_ERR_ALLOC;
+    }
 }
 
 } // extern "C"

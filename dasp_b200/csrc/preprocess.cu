@@ -23,7 +23,6 @@ enum { CAT_LONG = 0, CAT_MED = 1, CAT_1 = 2, CAT_3 = 3, CAT_4 = 4, CAT_2 = 5, CA
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_PASSES = 8;
 constexpr int TILE_ROWS = TILE_THREADS * TILE_PASSES;
-constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
 
 // same test order as the reference's if-chain (src/dasp_f64.h:502-530)
 __device__ __forceinline__ int category(int len, int block_longest)
@@ -104,6 +103,35 @@ __global__ void __launch_bounds__(TILE_THREADS) classify_scatter(const int *__re
     }
 }
 
+// Structural validation of the CSR input (the reference trusts its reader; a C ABI cannot): rowptr[0] == 0, rowptr
+// non-decreasing, rowptr[m] == nnz, every column in [0, n).  The same pass yields the column range of the matrix
+// (dasp_spmv_host uploads only that part of x).  out = {bad, min column, max column}.
+__global__ void __launch_bounds__(256) validate_csr(const int *__restrict__ rowptr, const int *__restrict__ colidx, int m, int n,
+                                                    long nnz, int *__restrict__ out)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    int bad = 0, lo = INT32_MAX, hi = -1;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i <= m; i += stride) {
+        const int a = rowptr[i];
+        if (i == 0 && a != 0) bad = 1;
+        if (i == m ? (long)a != nnz : a > rowptr[i + 1]) bad = 1;
+    }
+    for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const int c = colidx[k];
+        if (c < 0 || c >= n) bad = 1;
+        lo = min(lo, c); hi = max(hi, c);
+    }
+    for (int o = 16; o; o >>= 1) {
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(out, 1);
+        if (hi >= 0) { atomicMin(out + 1, lo); atomicMax(out + 2, hi); }
+    }
+}
+
 __global__ void gather_len(const int *__restrict__ rowptr, const int *__restrict__ rid, int cnt, int *__restrict__ len)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,40 +174,14 @@ __global__ void block_fill(const int *__restrict__ ml, int row_block, int blockn
     bsize[b] = size;
 }
 
-// P11: reference "warps" per long row and work units of this implementation
+// P11: reference "warps" per long row
 __global__ void long_warps(const int *__restrict__ rowptr, const int *__restrict__ rl, int row_long, int longw,
-                           int *__restrict__ wpr, int *__restrict__ upr)
+                           int *__restrict__ wpr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row_long) return;
     int len = rowptr[rl[i] + 1] - rowptr[rl[i]];
-    int w = (len + longw - 1) / longw;
-    wpr[i] = w;
-    upr[i] = (w + LONG_UNIT_WARPS - 1) / LONG_UNIT_WARPS;
-}
-
-// Execution order of the long-row work units.  Inside every group of 8 consecutive long rows the units are
-// enumerated chunk-major (chunk c of rows 8g..8g+7, then chunk c+1, ...), so the 8 warps of one CTA work on the
-// SAME slot range of 8 neighbouring long rows: rows that are long because they touch the same dense column range
-// (borders, constraints) then share their x sectors through that SM's L1.  Rows with fewer chunks simply drop out.
-__global__ void fill_long_units(const int *__restrict__ unit_first, int row_long, int *__restrict__ unit_row,
-                                int *__restrict__ unit_chunk)
-{
-    const int r0 = blockIdx.x * 8;
-    int n[8], base = unit_first[r0], most = 0;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        n[r] = (r0 + r < row_long) ? unit_first[r0 + r + 1] - unit_first[r0 + r] : 0;
-        most = max(most, n[r]);
-    }
-    for (int c = threadIdx.x; c < most; c += blockDim.x) {
-        int pos = base;
-#pragma unroll
-        for (int r = 0; r < 8; r++) pos += min(n[r], c);
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            if (n[r] > c) { unit_row[pos] = r0 + r; unit_chunk[pos] = c; pos++; }
-    }
+    wpr[i] = (len + longw - 1) / longw;
 }
 
 template <typename T>
@@ -324,74 +326,6 @@ __global__ void build_order(const int *__restrict__ cat_rid, const int *__restri
     order_rid[p] = v;
 }
 
-// one flag per 32 sorted medium rows: does any of them own an irregular tail?
-__global__ void flag_irreg(const int *__restrict__ irreg_rpt, int row_block, int ngroups, unsigned char *__restrict__ flag)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    int hi = min(32 * (g + 1), row_block);
-    flag[g] = irreg_rpt[hi] != irreg_rpt[32 * g];
-}
-
-// Resident compact form of reg_cid: one warp per 8-row block walks its tiles; per tile the smallest non-zero
-// column is the base and every slot stores (column - base) in 16 bits.  Column 0 (all padding slots, and genuine
-// entries of column 0) is the sentinel 0xFFFF, so the kernels gather exactly the x entries the reference layout
-// names.  A block with a tile spanning >= 65535 columns is flagged wide and keeps using reg_cid.
-__global__ void compress_cid(const int *__restrict__ blockPtr, const int *__restrict__ reg_cid, int blocknum,
-                             int *__restrict__ cbase, unsigned short *__restrict__ cdelta, unsigned char *__restrict__ wide)
-{
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= blocknum) return;
-    const int lane = threadIdx.x & 31;
-    const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
-    bool any_wide = false;
-    for (int p = bp0; p < bp1; p += 32) {
-        const int c = reg_cid[p + lane];
-        int mn = c ? c : INT32_MAX, mx = c;
-        for (int o = 16; o; o >>= 1) {
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
-        if (mn == INT32_MAX) mn = 0; // tile of zeros only
-        const bool ok = (mx - mn) < 65535;
-        any_wide |= !ok;
-        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
-        if (lane == 0) cbase[p >> 5] = mn;
-    }
-    if (lane == 0) wide[b] = any_wide ? 1 : 0;
-}
-
-// The same compact index form for the long part: one warp per work unit (execution order), one base per 32-slot
-// group; a unit with a group spanning >= 65535 columns is flagged wide and keeps using long_cid.
-__global__ void compress_long_cid(const int *__restrict__ unit_row, const int *__restrict__ unit_chunk,
-                                  const int *__restrict__ long_rpt_new, const int *__restrict__ long_cid, int n_units,
-                                  int longw, int unit_warps, int *__restrict__ cbase, unsigned short *__restrict__ cdelta,
-                                  unsigned char *__restrict__ wide)
-{
-    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= n_units) return;
-    const int lane = threadIdx.x & 31;
-    const int row = unit_row[u];
-    const long row_end = (long)long_rpt_new[row + 1] * longw;
-    const long beg = (long)long_rpt_new[row] * longw + (long)unit_chunk[u] * unit_warps * longw;
-    const long end = min(beg + (long)unit_warps * longw, row_end);
-    bool any_wide = false;
-    for (long p = beg; p < end; p += 32) {
-        const int c = long_cid[p + lane];
-        int mn = c ? c : INT32_MAX, mx = c;
-        for (int o = 16; o; o >>= 1) {
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
-        if (mn == INT32_MAX) mn = 0;
-        const bool ok = (mx - mn) < 65535;
-        any_wide |= !ok;
-        cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
-        if (lane == 0) cbase[p >> 5] = mn;
-    }
-    if (lane == 0) wide[u] = any_wide ? 1 : 0;
-}
-
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -444,6 +378,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply(int *__restrict_
     }
 }
 
+} // namespace
+
 int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st)
 {
     if (count <= 0) return DASP_OK;
@@ -460,14 +396,21 @@ int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st)
     return DASP_OK;
 }
 
-// ---- stable DESCENDING LSD radix sort of (key, value) pairs, 8 bits per pass (P8) ----
+namespace {
+
+// ---- stable LSD radix sort of (key, value) pairs, 8 bits per pass; DESCENDING for P8, ascending for derive.cu ----
 // Same scheme as the category partition above: per-tile digit histogram (digit-major), one exclusive scan, stable
 // scatter with in-warp ranks from __match_any_sync.  Descending order = ascending order of (255 - digit).
 constexpr int RS_BINS = 256;
 static_assert(RS_BINS == TILE_THREADS, "one thread per digit bin");
 
-__device__ __forceinline__ int rs_digit(int key, int shift) { return 255 - ((key >> shift) & 255); }
+template <bool DESC> __device__ __forceinline__ int rs_digit(int key, int shift)
+{
+    const int d = (key >> shift) & 255;
+    return DESC ? 255 - d : d;
+}
 
+template <bool DESC>
 __global__ void __launch_bounds__(TILE_THREADS) radix_count(const int *__restrict__ keys, int n, int shift, int ntiles,
                                                             int *__restrict__ counts)
 {
@@ -477,12 +420,13 @@ __global__ void __launch_bounds__(TILE_THREADS) radix_count(const int *__restric
     const long base = (long)blockIdx.x * TILE_ROWS;
     for (int p = 0; p < TILE_PASSES; p++) {
         long i = base + p * TILE_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&cnt[rs_digit(keys[i], shift)], 1);
+        if (i < n) atomicAdd(&cnt[rs_digit<DESC>(keys[i], shift)], 1);
     }
     __syncthreads();
     counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
+template <bool DESC>
 __global__ void __launch_bounds__(TILE_THREADS) radix_scatter(const int *__restrict__ keys_in, const int *__restrict__ vals_in, int n,
                                                               int shift, int ntiles, const int *__restrict__ offsets,
                                                               int *__restrict__ keys_out, int *__restrict__ vals_out)
@@ -500,7 +444,7 @@ __global__ void __launch_bounds__(TILE_THREADS) radix_scatter(const int *__restr
         const long i = row0 + p * TILE_THREADS + threadIdx.x;
         const bool live = i < n;
         const int key = live ? keys_in[i] : 0, val = live ? vals_in[i] : 0;
-        const int dg = live ? rs_digit(key, shift) : RS_BINS; // RS_BINS = "no element"
+        const int dg = live ? rs_digit<DESC>(key, shift) : RS_BINS; // RS_BINS = "no element"
         const unsigned same = __match_any_sync(0xffffffffu, dg);
         const int rank = __popc(same & ((1u << lane) - 1u));
         if (live && rank == 0) wcnt[warp][dg] = __popc(same);
@@ -520,9 +464,11 @@ __global__ void __launch_bounds__(TILE_THREADS) radix_scatter(const int *__restr
     }
 }
 
-// sorts `n` pairs by the low `bits` bits of the key, descending and stable; the result is in keys_out / vals_out
-int radix_sort_desc(DevicePool &tmp, const int *keys_in, const int *vals_in, int *keys_out, int *vals_out, int n, int bits,
-                    cudaStream_t st)
+} // namespace
+
+// sorts `n` pairs by the low `bits` bits of the key, stable; the result is in keys_out / vals_out
+int radix_sort_pairs(DevicePool &tmp, const int *keys_in, const int *vals_in, int *keys_out, int *vals_out, int n, int bits,
+                     bool descending, cudaStream_t st)
 {
     const int ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
     const int passes = (bits + 7) / 8;
@@ -536,13 +482,17 @@ int radix_sort_desc(DevicePool &tmp, const int *keys_in, const int *vals_in, int
     for (int p = 0; p < passes; p++) {
         // ping-pong so that the LAST pass lands in keys_out / vals_out
         int *ko = ((passes - 1 - p) & 1) ? kbuf : keys_out, *vo = ((passes - 1 - p) & 1) ? vbuf : vals_out;
-        radix_count<<<ntiles, TILE_THREADS, 0, st>>>(ki, n, 8 * p, ntiles, counts);
+        if (descending) radix_count<true><<<ntiles, TILE_THREADS, 0, st>>>(ki, n, 8 * p, ntiles, counts);
+        else radix_count<false><<<ntiles, TILE_THREADS, 0, st>>>(ki, n, 8 * p, ntiles, counts);
         DASP_TRY(scan_inplace(tmp, counts, RS_BINS * ntiles, st));
-        radix_scatter<<<ntiles, TILE_THREADS, 0, st>>>(ki, vi, n, 8 * p, ntiles, counts, ko, vo);
+        if (descending) radix_scatter<true><<<ntiles, TILE_THREADS, 0, st>>>(ki, vi, n, 8 * p, ntiles, counts, ko, vo);
+        else radix_scatter<false><<<ntiles, TILE_THREADS, 0, st>>>(ki, vi, n, 8 * p, ntiles, counts, ko, vo);
         ki = ko; vi = vo;
     }
     return DASP_OK;
 }
+
+namespace {
 
 template <typename T, bool F16>
 int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int *colidx, const T *val, cudaStream_t st)
@@ -567,6 +517,20 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(tmp.alloc((void **)&tile_counts, sizeof(int) * ((size_t)NCAT * ntiles + 1)));
     DASP_TRY(tmp.alloc((void **)&cat_rid, sizeof(int) * (size_t)(m + 1)));
     DASP_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int) * ((size_t)NCAT * ntiles + 1), st));
+    int *vflags = nullptr;
+    DASP_TRY(tmp.alloc((void **)&vflags, sizeof(int) * 4));
+    const int vinit[3] = {0, INT32_MAX, -1};
+    DASP_CUDA(cudaMemcpyAsync(vflags, vinit, sizeof(vinit), cudaMemcpyHostToDevice, st));
+    validate_csr<<<1184, 256, 0, st>>>(rowptr, colidx, m, n, (long)nnz, vflags);
+    int vres[3] = {0, 0, 0};
+    DASP_CUDA(cudaMemcpyAsync(vres, vflags, sizeof(vres), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    if (vres[0]) {
+        set_error("dasp_create: malformed CSR (rowptr must start at 0, be non-decreasing and end at nnz; columns must lie in [0, n))");
+        return DASP_ERR_INVALID;
+    }
+    s.col_min = vres[2] >= 0 ? vres[1] : 0;
+    s.col_max = vres[2] >= 0 ? vres[2] : -1;
     classify_count<<<ntiles, TILE_THREADS, 0, st>>>(rowptr, m, block_longest, ntiles, tile_counts);
     DASP_TRY(scan_inplace(tmp, tile_counts, NCAT * ntiles + 1, st));
     classify_scatter<<<ntiles, TILE_THREADS, 0, st>>>(rowptr, m, block_longest, ntiles, tile_counts, cat_rid);
@@ -613,34 +577,29 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         gather_len<<<grid_for(cm, 256), 256, 0, st>>>(rowptr, cat_rid + seg[CAT_MED], cm, len_in);
         int end_bit = 1;
         while (end_bit < 31 && (1 << end_bit) < block_longest) end_bit++;
-        DASP_TRY(radix_sort_desc(tmp, len_in, cat_rid + seg[CAT_MED], ml, ms, cm, end_bit, st));
+        DASP_TRY(radix_sort_pairs(tmp, len_in, cat_rid + seg[CAT_MED], ml, ms, cm, end_bit, true, st));
     }
 
     // ---- P12: block fill analysis -> blockPtr, irreg_rpt ; P11: long_rpt_new ----
     DASP_TRY(pool.alloc((void **)&L.blockPtr, sizeof(int) * (size_t)(blocknum + 1)));
     DASP_TRY(pool.alloc((void **)&L.irreg_rpt, sizeof(int) * (size_t)(cm + 1)));
     DASP_TRY(pool.alloc((void **)&L.long_rpt_new, sizeof(int) * (size_t)(cl + 1)));
-    DASP_TRY(pool.alloc((void **)&L.long_unit_first, sizeof(int) * (size_t)(cl + 1)));
     DASP_CUDA(cudaMemsetAsync(L.blockPtr, 0, sizeof(int) * (size_t)(blocknum + 1), st));
     DASP_CUDA(cudaMemsetAsync(L.irreg_rpt, 0, sizeof(int) * (size_t)(cm + 1), st));
     DASP_CUDA(cudaMemsetAsync(L.long_rpt_new, 0, sizeof(int) * (size_t)(cl + 1), st));
-    DASP_CUDA(cudaMemsetAsync(L.long_unit_first, 0, sizeof(int) * (size_t)(cl + 1), st));
     if (blocknum > 0) {
         const double need = h->threshold * 4 * 8; // same expression order as src/dasp_f64.h:1068
         block_fill<<<grid_for(blocknum, 128), 128, 0, st>>>(ml, cm, blocknum, need, F16 ? 1 : 0, L.blockPtr, L.irreg_rpt);
     }
     if (cl > 0)
-        long_warps<<<grid_for(cl, 256), 256, 0, st>>>(rowptr, cat_rid + seg[CAT_LONG], cl, LONGW, L.long_rpt_new,
-                                                      L.long_unit_first);
+        long_warps<<<grid_for(cl, 256), 256, 0, st>>>(rowptr, cat_rid + seg[CAT_LONG], cl, LONGW, L.long_rpt_new);
     DASP_TRY(scan_inplace(tmp, L.blockPtr, blocknum + 1, st));
     DASP_TRY(scan_inplace(tmp, L.irreg_rpt, cm + 1, st));
     DASP_TRY(scan_inplace(tmp, L.long_rpt_new, cl + 1, st));
-    DASP_TRY(scan_inplace(tmp, L.long_unit_first, cl + 1, st));
-    int tot[4];
+    int tot[3];
     DASP_CUDA(cudaMemcpyAsync(&tot[0], L.blockPtr + blocknum, sizeof(int), cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaMemcpyAsync(&tot[1], L.irreg_rpt + cm, sizeof(int), cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaMemcpyAsync(&tot[2], L.long_rpt_new + cl, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DASP_CUDA(cudaMemcpyAsync(&tot[3], L.long_unit_first + cl, sizeof(int), cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     if (tot[0] < 0 || tot[1] < 0 || tot[2] < 0) { set_error("padded layout exceeds 32-bit offsets"); return DASP_ERR_RANGE; }
@@ -651,7 +610,6 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     s.warp_number = s.BlockNum_long * 4;
     if ((int64_t)s.warp_number * LONGW > INT32_MAX) { set_error("padded long part exceeds 32-bit offsets"); return DASP_ERR_RANGE; }
     s.fill0_nnz_long = s.warp_number * LONGW;
-    L.n_long_units = tot[3];
 
     // ---- allocate the packed streams ----
     DASP_TRY(pool.alloc(&L.long_val, sizeof(T) * (size_t)s.fill0_nnz_long));
@@ -663,24 +621,11 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(pool.alloc(&L.short_val, sizeof(T) * (size_t)s.fill0_nnz_short));
     DASP_TRY(pool.alloc((void **)&L.short_cid, sizeof(int) * (size_t)s.fill0_nnz_short));
     DASP_TRY(pool.alloc((void **)&L.order_rid, sizeof(int) * (size_t)m));
-    DASP_TRY(pool.alloc((void **)&L.long_unit_row, sizeof(int) * (size_t)L.n_long_units));
-    DASP_TRY(pool.alloc((void **)&L.long_unit_chunk, sizeof(int) * (size_t)L.n_long_units));
-    DASP_TRY(pool.alloc(&L.long_partial, 8 * (size_t)L.n_long_units));
-    DASP_TRY(pool.alloc((void **)&L.long_done, sizeof(unsigned) * (size_t)cl));
-    const int ngroups = ceil_div(cm, 32);
-    DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
-    DASP_TRY(pool.alloc((void **)&L.long_cbase, sizeof(int) * (size_t)(s.fill0_nnz_long / 32)));
-    DASP_TRY(pool.alloc((void **)&L.long_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_long));
-    DASP_TRY(pool.alloc((void **)&L.long_wide, (size_t)L.n_long_units));
-    DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
-    DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
-    DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
     DASP_CUDA(cudaMemsetAsync(L.long_val, 0, sizeof(T) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.long_cid, 0, sizeof(int) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.short_val, 0, sizeof(T) * (size_t)s.fill0_nnz_short, st));
     DASP_CUDA(cudaMemsetAsync(L.short_cid, 0, sizeof(int) * (size_t)s.fill0_nnz_short, st));
     DASP_CUDA(cudaMemsetAsync(L.irreg_val, 0, sizeof(T) * (size_t)s.fill0_nnz_irreg, st));
-    DASP_CUDA(cudaMemsetAsync(L.long_done, 0, sizeof(unsigned) * (size_t)cl, st));
 
     // ---- P6: short rows ----
     ShortGeom sg;
@@ -702,23 +647,15 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         if (per_row > 64) per_row = 64;
         pack_long<T><<<dim3(cl, per_row), 256, 0, st>>>(rowptr, colidx, val, cat_rid + seg[CAT_LONG], L.long_rpt_new, LONGW,
                                                         (T *)L.long_val, L.long_cid);
-        fill_long_units<<<(cl + 7) / 8, 128, 0, st>>>(L.long_unit_first, cl, L.long_unit_row, L.long_unit_chunk);
-        compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.long_cid,
-                                                                                   L.n_long_units, LONGW, LONG_UNIT_WARPS, L.long_cbase,
-                                                                                   L.long_cdelta, L.long_wide);
     }
     // ---- P13/P14: medium rows ----
     if (cm > 0) {
         pack_irreg<T><<<grid_for(cm, 256), 256, 0, st>>>(rowptr, colidx, val, ms, L.irreg_rpt, cm, (T *)L.irreg_val,
                                                           L.irreg_cid);
-        flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
     }
     if (blocknum > 0)
         pack_reg<T, F16><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(rowptr, colidx, val, ms, ml, L.blockPtr, L.irreg_rpt,
                                                                                cm, blocknum, (T *)L.reg_val, L.reg_cid);
-    if (blocknum > 0)
-        compress_cid<<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(L.blockPtr, L.reg_cid, blocknum, L.reg_cbase,
-                                                                          L.reg_cdelta, L.blk_wide);
     // ---- P10: order_rid ----
     OrderGeom og;
     og.cl = cl; og.cm = cm; og.n1 = n1; og.c13 = c13; og.n3 = n3; og.c4 = c4; og.c2 = c2; og.c0 = c0;
@@ -762,6 +699,10 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     s.data_X2 = ((int64_t)m + nnz) * ev + common;
     s.data_origin1 = (nnz + (int64_t)n + m) * ev + nnz * ei + ((int64_t)m + 1) * ei;
 
+    DASP_CUDA(cudaGetLastError());
+    // everything the kernels read that is NOT part of the reference layout (work units, compact indices, column-blocked
+    // copy of scattered long rows, inverse permutation) is derived from the arrays above; dasp_load runs the same step
+    DASP_TRY(derive(h, st));
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

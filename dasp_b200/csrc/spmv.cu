@@ -32,7 +32,6 @@ namespace {
 
 constexpr int CTA = 256;
 constexpr int WARPS = CTA / 32;
-constexpr int LONG_UNIT_WARPS = 32; // must match preprocess.cu
 constexpr int SINGLES_PER_THREAD = 4;
 constexpr int SHORT_TILES_PER_WARP = 4;
 #ifndef MED_TB
@@ -81,6 +80,13 @@ struct SpmvArgs {
     int y1, y13, y34, y22, y0; // y bases (K11)
     int G;                     // 8 (f64) / 32 (f16)
     int row_zero;
+    // column-blocked long rows (LCB, derive.cu)
+    const void *lcb_val;
+    const unsigned short *lcb_col, *lcb_row;
+    const int *lcb_blk_ptr, *lcb_cta_first;
+    void *lcb_acc;
+    unsigned *lcb_done;
+    int lcb_bw_log2, lcb_nblk, lcb_nctas, ncols;
     int e[7];      // exclusive CTA-range end of category k (long, medium, singles, 1&3, 3/4, 2&2, zero)
     long items[7]; // warp-level work items of category k
 };
@@ -811,6 +817,126 @@ __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __
     run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * WARPS + warp, dyn_smem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// long rows, column-blocked (LCB): for long rows whose columns are scattered over x every gather of the chunked kernel
+// above costs its own 128-byte L1 wavefront and its own 32-byte DRAM sector.  Here the live entries of ALL long rows
+// are sorted by (column block, row) at preprocessing (derive.cu); a CTA owns up to LCB_PART consecutive entries of one
+// block, stages that block of x (64 KB) in shared memory with TMA bulk copies (cp.async.bulk + mbarrier) while its
+// first value / index loads are in flight, and gathers from shared memory.  Every warp walks a contiguous slice; while
+// the row stays the same the lanes accumulate privately, a row change costs one warp reduction and one atomic add into
+// the per-row accumulator (the atomic merge of split rows, cf. longPart_sum src/dasp_f64.h:53-75).  The last CTA to
+// finish turns the accumulators into y (K11 placement, scatter / axpby forms included) and re-zeroes them.
+template <typename A> __device__ __forceinline__ void red_add(A *p, A v) { atomicAdd(p, v); }
+
+template <typename T>
+__global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ SpmvArgs a)
+{
+    using A = typename Acc<T>::type;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    T *xs = reinterpret_cast<T *>(dyn_smem);
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_last;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int blo = 0, bhi = a.lcb_nblk; // last block b with cta_first[b] <= c (empty blocks share their successor's value)
+    while (bhi - blo > 1) {
+        const int mid = (blo + bhi) >> 1;
+        if (__ldg(a.lcb_cta_first + mid) <= c) blo = mid; else bhi = mid;
+    }
+    const int b = blo;
+    const long col0 = (long)b << a.lcb_bw_log2;
+    const int cnt = (int)min(1L << a.lcb_bw_log2, (long)a.ncols - col0);
+    const T *xg = static_cast<const T *>(a.x) + col0;
+    const uint32_t bytes16 = ((uint32_t)cnt * (uint32_t)sizeof(T)) & ~15u;
+    const uint32_t bar_addr = smem_u32(&bar);
+    if (tid == 0) {
+        mbar_init(bar_addr, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep)); // other CTAs read the same block
+        mbar_expect_tx(bar_addr, bytes16);
+        for (uint32_t off = 0; off < bytes16; off += 32768u)
+            bulk_g2s(smem_u32(xs) + off, reinterpret_cast<const char *>(xg) + off, min(32768u, bytes16 - off), bar_addr, keep);
+    }
+    for (int i = (int)(bytes16 / sizeof(T)) + tid; i < cnt; i += CTA) xs[i] = xg[i]; // tail that is not a 16-byte multiple
+
+    const int p0 = __ldg(a.lcb_blk_ptr + b), p1 = __ldg(a.lcb_blk_ptr + b + 1);
+    const int beg = p0 + (c - __ldg(a.lcb_cta_first + b)) * LCB_PART, end = min(beg + LCB_PART, p1);
+    const int per = ((end - beg + WARPS * 32 - 1) / (WARPS * 32)) * 32;
+    const int wbeg = beg + warp * per, wend = min(wbeg + per, end);
+    const T *val = static_cast<const T *>(a.lcb_val);
+    const StreamPol pol = make_stream_policy<false>();
+    constexpr int U = 4;
+    T v0[U], v1[U];
+    int c0[U], c1[U], r0[U], r1[U];
+    auto load = [&](T(&v)[U], int(&cc)[U], int(&rr)[U], int i) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int q = i + 32 * u + lane;
+            const bool ok = q < wend;
+            v[u] = ok ? ld_stream1(val + q, pol) : T(0);
+            cc[u] = ok ? ld_stream1(a.lcb_col + q, pol) : 0;
+            rr[u] = ok ? ld_stream1(a.lcb_row + q, pol) : -1;
+        }
+    };
+    A *acc = static_cast<A *>(a.lcb_acc);
+    A lane_acc = 0;
+    int cur = -1;
+    auto flush = [&]() {
+        if (cur >= 0) {
+            const A t = warp_sum(lane_acc);
+            if (lane == 0) red_add(acc + cur, t);
+        }
+        lane_acc = 0;
+        cur = -1;
+    };
+    auto consume = [&](const T(&v)[U], const int(&cc)[U], const int(&rr)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            A p = to_acc(v[u]) * to_acc(xs[cc[u]]);
+            const int r = rr[u];
+            if (__all_sync(0xffffffffu, r == cur)) { lane_acc += p; continue; }
+            flush();
+            const int rf = __shfl_sync(0xffffffffu, r, 0);
+            if (rf >= 0 && __all_sync(0xffffffffu, r == rf)) { cur = rf; lane_acc = p; continue; }
+            // several rows in this group (rows ascend inside a block): segmented reduction towards the head lane of every run
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const A q = __shfl_down_sync(0xffffffffu, p, o);
+                const int rq = __shfl_down_sync(0xffffffffu, r, o);
+                if (lane + o < 32 && rq == r) p += q;
+            }
+            const int rp = __shfl_up_sync(0xffffffffu, r, 1);
+            if ((lane == 0 || rp != r) && r >= 0) red_add(acc + r, p);
+        }
+    };
+    load(v0, c0, r0, wbeg);
+    mbar_wait(bar_addr, 0);
+    __syncthreads(); // the tail elements written with plain stores
+    for (int i = wbeg; i < wend; i += 64 * U) {
+        load(v1, c1, r1, i + 32 * U);
+        consume(v0, c0, r0);
+        load(v0, c0, r0, i + 64 * U);
+        consume(v1, c1, r1);
+    }
+    flush();
+    // completion: the last CTA of the launch writes y for every long row and re-arms the scratch
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.lcb_done, 1u) == (unsigned)(a.lcb_nctas - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int r = tid; r < a.row_long; r += CTA) {
+        const A t = __ldcg(acc + r);
+        store_y<T>(a, r, t);
+        __stcg(acc + r, A(0));
+    }
+    if (tid == 0) *a.lcb_done = 0u;
+}
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- power-iteration helpers ---------------------------------------------------------------------
@@ -855,12 +981,6 @@ __global__ void __launch_bounds__(256) scale_rsqrt(double *__restrict__ v, long 
 } // namespace
 
 namespace {
-__global__ void __launch_bounds__(256) invert_order(const int *__restrict__ order, int m, int *__restrict__ inv)
-{
-    int k = blockIdx.x * 256 + threadIdx.x;
-    if (k < m) inv[order[k]] = k;
-}
-
 struct UnpermArgs {
     const void *y_perm;
     const int *inv;
@@ -890,10 +1010,6 @@ int unpermute_to(dasp_handle *h, const void *d_y_perm, const ScatterTo &dst, voi
     Layout &L = h->L;
     const int m = L.s.m;
     if (m == 0) return DASP_OK;
-    if (!L.inv_order) {
-        DASP_TRY(h->pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
-        invert_order<<<cdiv(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
-    }
     UnpermArgs a{};
     a.y_perm = d_y_perm; a.inv = L.inv_order; a.m = m; a.row_offset = (long)dst.row_offset; a.rs_ptr = dst.norm2;
     a.dest[0] = first;
@@ -906,7 +1022,18 @@ int unpermute_to(dasp_handle *h, const void *d_y_perm, const ScatterTo &dst, voi
     return DASP_OK;
 }
 
-int launches_per_spmv(const dasp_handle *) { return 1; }
+static bool lcb_selected(const dasp_handle *h)
+{
+    return h->L.lcb_nctas > 0 && (h->category_mask & 1) &&
+           (h->var_long == DASP_VARIANT_BLOCKED || (h->var_long == DASP_VARIANT_AUTO && h->lcb_auto));
+}
+
+int launches_per_spmv(const dasp_handle *h)
+{
+    if (!lcb_selected(h)) return 1;
+    const dasp_stats_t &s = h->L.s;
+    return (s.m - s.row_long > 0 && (h->category_mask & 14)) ? 2 : 1;
+}
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
 {
@@ -1020,7 +1147,23 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const int tiles13 = cdiv(s.common_13, 8), tiles34 = cdiv(s.short_row_34, 8);
     const int tiles22 = cdiv(s.short_row_2, 2 * a.G) * (a.G / 8);
     const int cm = h->category_mask;
-    const int on_long = cm & 1, on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1, on_zero = (cm >> 3) & 1;
+    // scattered long rows: the column-blocked kernel (its own launch: 64 KB of shared memory per CTA would take the L1
+    // away from the x gathers of the other categories); needs x on a 16-byte boundary for the TMA copies
+    const bool use_lcb = lcb_selected(h) && ((uintptr_t)d_x & 15) == 0;
+    if (use_lcb) {
+        a.lcb_val = L.lcb_val; a.lcb_col = L.lcb_col; a.lcb_row = L.lcb_row; a.lcb_blk_ptr = L.lcb_blk_ptr;
+        a.lcb_cta_first = L.lcb_cta_first; a.lcb_acc = L.lcb_acc; a.lcb_done = L.lcb_done;
+        a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = s.n;
+        if (!h->lcb_attr_set) {
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
+            h->lcb_attr_set = 1;
+        }
+        if (f16) lcb_kernel<__half><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
+        else lcb_kernel<double><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
+        DASP_CUDA(cudaGetLastError());
+    }
+    const int on_long = (cm & 1) && !use_lcb, on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1, on_zero = (cm >> 3) & 1;
     // medium variant: AUTO = one lane per row.  The 4-lanes-per-row split (the analogue of the reference's
     // rowloop=1 geometry for small matrices, src/dasp_f64.h:533-536) and the DMMA tiles are kept as measured
     // alternatives: both lose on B200 (profiles/r01/variants.md).
@@ -1028,8 +1171,8 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     int med = 0;
     if (h->var_medium == DASP_VARIANT_MMA && !f16) med = 1;
     else if (h->var_medium == DASP_VARIANT_SPLIT) med = 2;
-    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA;
-    const bool tma_long = h->var_long == DASP_VARIANT_TMA;
+    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA && !use_lcb;
+    const bool tma_long = h->var_long == DASP_VARIANT_TMA && !use_lcb;
     const bool mma_short = !f16 && h->var_short == DASP_VARIANT_MMA;
     a.items[0] = on_long * (long)L.n_long_units;
     a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);

@@ -92,11 +92,88 @@ __device__ inline int skewed_len(const dasp_synth_spec &s, int64_t i)
     return 1 + (int)(h3(s.seed, (uint64_t)i, 0x52ull) & 3);
 }
 
+// ---- SURVEY.md §8(d)-literal generators (kinds 4, 5): columns in RANDOM order, distinct within a row ----
+// A keyed bijection of [0, 2^bits): odd multiplications, additions and xor-shifts are each invertible on a fixed
+// width, so distinct inputs give distinct outputs ("uniform without replacement", evaluated per element).
+__device__ inline uint64_t perm_pow2(uint64_t x, int bits, uint64_t key)
+{
+    const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+    const int sh = bits > 1 ? bits / 2 : 1;
+    const uint64_t k1 = mix(key), k2 = mix(k1), k3 = mix(k2);
+    x = (x * (k1 | 1) + (k1 >> 32)) & mask;
+    x ^= x >> sh;
+    x = (x * (k2 | 1) + (k2 >> 32)) & mask;
+    x ^= x >> sh;
+    x = (x * (k3 | 1) + (k3 >> 32)) & mask;
+    x ^= x >> sh;
+    return x;
+}
+// the same on [0, size), size <= 2^bits: cycle walking (expected < 2 rounds)
+__device__ inline int64_t perm_range(int64_t j, int64_t size, uint64_t key)
+{
+    int bits = 1;
+    while ((1ll << bits) < size) bits++;
+    uint64_t x = (uint64_t)j;
+    do x = perm_pow2(x, bits, key); while ((int64_t)x >= size);
+    return (int64_t)x;
+}
+// window of `width` columns centred on the diagonal position of row i, clipped to [0, n)
+__device__ inline int64_t window_lo(const dasp_synth_spec &s, int64_t i, int64_t width)
+{
+    int64_t c = (int64_t)((double)i * (double)s.n / (double)s.m);
+    int64_t lo = c - width / 2;
+    if (lo > s.n - width) lo = s.n - width;
+    if (lo < 0) lo = 0;
+    return lo;
+}
+
+// kind 5: one long row per stride of m / n_long rows, at a hashed position inside its stride
+__device__ inline bool skewed_spec_is_long(const dasp_synth_spec &s, int64_t i)
+{
+    if (s.n_long <= 0) return false;
+    const int64_t stride = s.m / s.n_long, j = i / stride;
+    if (j >= s.n_long) return false;
+    return i == j * stride + (int64_t)(h3(s.seed, (uint64_t)j, 0x10c5ull) % (uint64_t)stride);
+}
+__device__ inline int spec_len(const dasp_synth_spec &s, int64_t i)
+{
+    if (s.kind == 4) return powerlaw_len(s, i);
+    if (skewed_spec_is_long(s, i)) return s.long_len;
+    return 1 + (int)(h3(s.seed, (uint64_t)i, 0x52ull) & 3);
+}
+// column of element k of row i (length len)
+__device__ inline int64_t spec_col(const dasp_synth_spec &s, int64_t i, int64_t k, int len)
+{
+    const uint64_t key = h3(s.seed ^ 0xc01ull, (uint64_t)i, 0x77ull);
+    if (s.kind == 5 && len == s.long_len && skewed_spec_is_long(s, i)) return perm_range(k, s.n, key); // uniform over all columns
+    if (s.kind == 5) { // short rows: distinct columns of the +-window window
+        int64_t D = 2 * (int64_t)s.window;
+        if (D > s.n) D = s.n;
+        return window_lo(s, i, D) + perm_range(k, D, key);
+    }
+    // kind 4: every 10th element is a global column outside the window, the others are distinct columns of the window
+    // (2*window wide; enlarged to the next power of two >= twice the windowed count for rows that would not fit)
+    const int64_t lg = len / 10, lw = len - lg;
+    int64_t D = 2 * (int64_t)s.window;
+    while (D < 2 * lw) D <<= 1;
+    if (D > s.n) D = s.n;
+    const int64_t lo = window_lo(s, i, D);
+    const bool glob = (k % 10 == 9) && (s.n - D >= 2 * lg);
+    if (glob) {
+        const int64_t q = perm_range(k / 10, s.n - D, key ^ 0x9e37ull);
+        return q < lo ? q : q + D;
+    }
+    // windowed element index: elements that are not global keep their rank; if the global part had to be folded into
+    // the window (tiny n), every element is windowed and k itself is the rank
+    const int64_t j = (s.n - D >= 2 * lg) ? k - k / 10 : k;
+    return lo + perm_range(j, D, key);
+}
+
 __global__ void plsk_len(dasp_synth_spec s, int64_t row0, int64_t rows, int *len)
 {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= rows) return;
-    len[t] = s.kind == 1 ? powerlaw_len(s, row0 + t) : skewed_len(s, row0 + t);
+    len[t] = s.kind == 1 ? powerlaw_len(s, row0 + t) : (s.kind == 2 ? skewed_len(s, row0 + t) : spec_len(s, row0 + t));
 }
 
 // Windowed columns of a row are an ASCENDING sequence of distinct points of a window centred on the
@@ -132,7 +209,9 @@ __global__ void plsk_fill(dasp_synth_spec s, int64_t row0, int64_t rows, const i
     const int64_t t = lo, i = row0 + t, k = e - rowptr[t];
     const int len = rowptr[t + 1] - rowptr[t];
     int64_t col;
-    if (s.kind == 2 && i < s.n_long) {
+    if (s.kind >= 4) {
+        col = spec_col(s, i, k, len);
+    } else if (s.kind == 2 && i < s.n_long) {
         // long rows of the skewed matrix: ascending, distinct, one entry per stripe of band/len columns of a
         // band shared by all long rows (each row starts at its own hashed shift inside the first stripe)
         double stripe = (double)s.band / (double)len;
@@ -214,7 +293,9 @@ int dasp_synth_rowlen(const dasp_synth_spec *spec, int64_t row0, int64_t row1, i
     switch (spec->kind) {
     case 0: stencil_len<<<blocks(rows, 256), 256, 0, st>>>(*spec, row0, rows, d_len); break;
     case 1:
-    case 2: plsk_len<<<blocks(rows, 256), 256, 0, st>>>(*spec, row0, rows, d_len); break;
+    case 2:
+    case 4:
+    case 5: plsk_len<<<blocks(rows, 256), 256, 0, st>>>(*spec, row0, rows, d_len); break;
     case 3: band_kernel<false><<<blocks(rows * 32, 256), 256, 0, st>>>(*spec, row0, rows, d_len, nullptr, nullptr, nullptr); break;
     default: snprintf(g_err, sizeof(g_err), "unknown kind %d", spec->kind); return -1;
     }
@@ -232,7 +313,9 @@ int dasp_synth_fill(const dasp_synth_spec *spec, int64_t row0, int64_t row1, con
     switch (spec->kind) {
     case 0: stencil_fill<<<blocks(rows, 128), 128, 0, st>>>(*spec, row0, rows, d_rowptr, d_colidx, d_val); break;
     case 1:
-    case 2: {
+    case 2:
+    case 4:
+    case 5: {
         int nnz = 0;
         cudaError_t e = cudaMemcpyAsync(&nnz, d_rowptr + rows, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

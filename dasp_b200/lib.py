@@ -27,7 +27,8 @@ _STATS_INT = [
 class _Stats(C.Structure):
     _fields_ = ([(n, C.c_int64 if n == "nnz" else C.c_int) for n in _STATS_INT]
                 + [("rate_fill0", C.c_double), ("data_X", C.c_int64), ("data_X2", C.c_int64),
-                   ("data_origin1", C.c_int64), ("preprocess_ms", C.c_double), ("device_bytes", C.c_int64)])
+                   ("data_origin1", C.c_int64), ("preprocess_ms", C.c_double), ("device_bytes", C.c_int64),
+                   ("col_min", C.c_int), ("col_max", C.c_int)])
 
 
 ARRAYS = ["order_rid", "long_rpt_new", "long_val", "long_cid", "blockPtr", "irreg_rpt", "irreg_val",

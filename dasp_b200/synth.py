@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-STENCIL27, POWERLAW, SKEWED, BANDED = 0, 1, 2, 3
+STENCIL27, POWERLAW, SKEWED, BANDED, POWERLAW_SPEC, SKEWED_SPEC = 0, 1, 2, 3, 4, 5
 
 
 class Spec(C.Structure):
@@ -38,6 +38,18 @@ def skewed(n_long=1000, long_len=1_000_000, n_short=50_000_000, window=4096, see
     band = min(band, 1 << (m.bit_length() - 1))
     return Spec(kind=SKEWED, m=m, n=m, seed=seed, n_long=n_long, long_len=long_len, window=window,
                 band_lo=(m - band) // 2, band=band)
+
+
+def powerlaw_spec(m=10_000_000, alpha=0.95, lmax=1_000_000, window=4096, seed=20240001) -> Spec:
+    """C3 exactly as SURVEY.md §8(d) words it: unsorted distinct columns, 90 % in the +-4096 window, 10 % global."""
+    return Spec(kind=POWERLAW_SPEC, m=m, n=m, seed=seed, alpha=alpha, lmax=min(lmax, m // 2), window=window)
+
+
+def skewed_spec(n_long=1000, long_len=1_000_000, n_short=50_000_000, window=4096, seed=20240005) -> Spec:
+    """C5 exactly as SURVEY.md §8(d) words it: long rows at seeded positions with columns uniform over n without
+    replacement, short rows with distinct random columns of the +-4096 window."""
+    m = n_long + n_short
+    return Spec(kind=SKEWED_SPEC, m=m, n=m, seed=seed, n_long=n_long, long_len=min(long_len, m // 2), window=window)
 
 
 def banded(m=121_192, mean_len=22, window=2048, seed=7) -> Spec:

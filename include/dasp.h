@@ -18,7 +18,11 @@
  *
  * Conventions: plain pointers and sizes only; every entry returns 0 on success or a negative
  * dasp_status (the reference checks no CUDA status at all: SURVEY.md §5); a handle is used by one
- * host thread at a time, distinct handles (one per GPU) are independent; the library owns all
+ * host thread at a time and admits ONE in-flight product at a time (the merge scratch of split long
+ * rows belongs to the handle: do not overlap two products of the same handle on different streams
+ * or replay a captured graph concurrently with itself); distinct handles (one per GPU, or several
+ * per GPU) are independent.  Every entry selects the handle's device itself and restores the caller's
+ * current device before returning.  The library owns all
  * device memory of a handle, the caller owns x, y and the CSR arrays.  There is no CPU fallback:
  * without a CUDA device every entry fails with DASP_ERR_CUDA.
  */
@@ -52,7 +56,10 @@ typedef enum {
     DASP_VARIANT_CUDA_CORE = 1, /* per-lane 4-wide dot over the 8x4 tiles, 256/128-bit loads */
     DASP_VARIANT_MMA = 2,       /* mma.sync m8n8k4.f64 (DMMA) on the same tiles, as the reference does */
     DASP_VARIANT_SPLIT = 3,     /* medium rows only: CUDA-core, four lanes per row (small, latency-bound matrices) */
-    DASP_VARIANT_TMA = 4        /* long rows only: CUDA-core fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier ring) */
+    DASP_VARIANT_TMA = 4,       /* long rows only: CUDA-core fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier ring) */
+    DASP_VARIANT_BLOCKED = 5    /* long rows only: column-blocked copy of the long part, x blocks staged in shared memory by
+                                   TMA bulk copies, atomic merge of the split rows; AUTO picks it when the long rows'
+                                   gathers are scattered (built on demand otherwise; needs row_long <= 65535) */
 } dasp_variant;
 
 /* The reference's locals that describe the layout (the 18 structure columns of its CSV record,
@@ -76,12 +83,16 @@ typedef struct dasp_stats_t {
     int64_t data_origin1;    /* CSR ("algorithmic") bytes, src/main_f64.cu:143                 */
     double preprocess_ms;    /* device time of the GPU preprocessing inside dasp_create        */
     int64_t device_bytes;    /* device memory held by the handle                               */
+    int col_min, col_max;    /* smallest / largest column index present (col_max = -1: no entries): the
+                                only part of x a product reads; dasp_spmv_host uploads just that range */
 } dasp_stats_t;
 
 /* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,
  * src/dasp_f16.h:1029-1443) and keep the packed layout resident.  rowptr/colidx/val may be host
  * or device pointers (detected); val is double[nnz] or IEEE-half[nnz] by dtype; columns need not
- * be sorted.  threshold/block_longest: the reference's run-time constants 0.75 / 256
+ * be sorted.  The CSR is validated (rowptr starts at 0, is non-decreasing and ends at nnz; columns in
+ * [0, n)): DASP_ERR_INVALID otherwise.  Device-resident inputs must not be modified during the call
+ * (the call waits for work already queued on the device before it reads them).  threshold/block_longest: the reference's run-time constants 0.75 / 256
  * (src/main_f64.cu:124-125).  The CSR is not retained. */
 int dasp_create(dasp_handle **h, dasp_dtype dtype, int device, int m, int n, int64_t nnz,
                 const int *rowptr, const int *colidx, const void *val, double threshold,
@@ -109,7 +120,8 @@ int dasp_save(const dasp_handle *h, const char *path);
 int dasp_load(dasp_handle **h, const char *path, int device);
 
 /* Host-buffer convenience with the reference's data movement (src/dasp_f64.h:1241,1402): upload x,
- * run, download y (permuted order), synchronous. */
+ * run, download y (permuted order), synchronous.  Only x[col_min .. col_max] (dasp_stats) is uploaded:
+ * the product reads nothing else, and a row slab of a banded matrix touches a fraction of x. */
 int dasp_spmv_host(dasp_handle *h, const void *x_host, void *y_host);
 
 /* Host buffers, `count` independent products y_j = A*x_j (several right-hand sides, or a stream of requests):
@@ -146,7 +158,7 @@ int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *o
 int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes,
                 int64_t *bytes);
 
-/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA;  short_rows: AUTO | CUDA_CORE | MMA
+/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA
  * (FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 

@@ -21,7 +21,15 @@ extern "C" {
 #endif
 
 typedef struct dasp_synth_spec {
-    int kind;        /* 0 stencil27, 1 powerlaw, 2 skewed, 3 banded-symmetric (cop20k_A stand-in) */
+    int kind;        /* 0 stencil27, 1 powerlaw, 2 skewed, 3 banded-symmetric (cop20k_A stand-in),
+                        4 powerlaw_spec, 5 skewed_spec: the generators of SURVEY.md 8(d) taken literally — columns in
+                        RANDOM order, distinct within a row (keyed bijections, evaluated per element):
+                        4: same row lengths as kind 1; 9 of 10 elements uniform in the +-window window around i*n/m
+                           (window enlarged to a power of two >= 2x the windowed count for rows that do not fit), every
+                           10th element a uniform global column outside the window;
+                        5: n_long rows of long_len entries at seeded positions (one per stride of m/n_long rows), columns
+                           uniform over all n without replacement; the other rows have L uniform in {1,2,3,4} with distinct
+                           random columns of the +-window window */
     int64_t m, n;    /* global rows / columns */
     uint64_t seed;
     /* stencil27: grid nx*ny*nz, natural ordering (x fastest), columns ascending */
