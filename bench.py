@@ -39,10 +39,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5", "c3_spec", "c5_spec"])
     ap.add_argument("--grid", type=int, default=256, help="c4: stencil grid edge")
     ap.add_argument("--scale", type=float, default=1.0, help="c3/c5: fraction of the named size")
-    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split", "tma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split", "tma", "blocked"])
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
@@ -76,10 +76,15 @@ def make_spec(args):
         return synth.banded(), ("C2" if half else "C1") + " cop20k_A stand-in (banded symmetric, seed 7; real .mtx is a missing blob) " + ("fp16" if half else "fp64"), half
     if w == "c3":
         m = int(10_000_000 * args.scale)
-        return synth.powerlaw(m=m), f"C3 power-law alpha=0.95 {m} rows fp64", False
+        return synth.powerlaw(m=m), f"C3 power-law alpha=0.95 {m} rows, CSR-sorted variant (ascending windowed columns) fp64", False
+    if w == "c3_spec":
+        m = int(10_000_000 * args.scale)
+        return synth.powerlaw_spec(m=m), f"C3 power-law alpha=0.95 {m} rows as SURVEY 8(d) words it (unsorted distinct columns: 90% +-4096 window, 10% global) fp64", False
     m = int(50_000_000 * args.scale)
     nl = max(1, int(1000 * args.scale))
-    return synth.skewed(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows (ascending columns, 50% of a common 2^21 band) + {m} short rows fp64", False
+    if w == "c5_spec":
+        return synth.skewed_spec(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows at seeded positions, columns uniform over n without replacement, + {m} short rows (unsorted, +-4096 window) as SURVEY 8(d) words it fp64", False
+    return synth.skewed(n_long=nl, n_short=m), f"C5 skewed {nl}x1M long rows, CSR-sorted variant (ascending columns, 50% of a common 2^21 band) + {m} short rows fp64", False
 
 
 def algorithmic_bytes(m, n, nnz, esz):
@@ -151,17 +156,39 @@ def ncu_traffic(args):
 
 
 def device_check(rp, ci, v, x, y_orig, rows):
-    """Relative L2 error of the first `rows` entries of y (original row order) against an independent evaluation of the
-    CSR definition on the device in float64 (torch index_add; no code of this repository, no oracle)."""
+    """Relative L2 error of ALL `rows` entries of y (original row order) against an independent evaluation of the CSR
+    definition on the device in float64 (torch index_add_ in row chunks of at most 2^27 entries; no code of this
+    repository, no oracle)."""
     import torch
 
-    k = int(rp[rows].item())
-    row_of = torch.repeat_interleave(torch.arange(rows, device=rp.device), (rp[1:rows + 1] - rp[:rows]).long())
-    prod = v[:k].double() * x.double()[ci[:k].long()]
-    ref = torch.zeros(rows, dtype=torch.float64, device=rp.device).index_add_(0, row_of, prod)
-    num = torch.linalg.vector_norm(y_orig[:rows].double() - ref)
-    den = torch.linalg.vector_norm(ref).clamp_min(1e-300)
-    return float((num / den).item())
+    num = torch.zeros((), dtype=torch.float64, device=rp.device)
+    den = torch.zeros((), dtype=torch.float64, device=rp.device)
+    xd = x.double()
+    r0 = 0
+    while r0 < rows:
+        target = rp[r0:r0 + 1].long() + (1 << 27)
+        r1 = int(torch.searchsorted(rp, target.to(rp.dtype), right=True).item()) - 1
+        r1 = min(rows, max(r1, r0 + 1))
+        k0, k1 = int(rp[r0].item()), int(rp[r1].item())
+        ref = torch.zeros(r1 - r0, dtype=torch.float64, device=rp.device)
+        if k1 > k0:
+            row_of = torch.repeat_interleave(torch.arange(r1 - r0, device=rp.device), (rp[r0 + 1:r1 + 1] - rp[r0:r1]).long())
+            ref.index_add_(0, row_of, v[k0:k1].double() * xd[ci[k0:k1].long()])
+            del row_of
+        num += ((y_orig[r0:r1].double() - ref) ** 2).sum()
+        den += (ref ** 2).sum()
+        r0 = r1
+    return float((num.sqrt() / den.sqrt().clamp_min(1e-300)).item())
+
+
+def config_dict(args, spec, wname, m, n, nnz_total, world, b_alg_rank, small, cold):
+    """The `config` object of the JSON line; both arms (ours / --impl reference) print the same one."""
+    return {"workload": wname, "m": m, "n": n, "nnz": nnz_total, "seed": int(spec.seed),
+            "partition": "nnz-balanced contiguous row slabs, x replicated" if world > 1 else "single GPU",
+            "l2": ("L2 flushed before every launch" if (small and cold) else
+                   ("inputs exceed L2 (%.0f MB per rank)" % (b_alg_rank / 1e6) if not small else
+                    "warm L2: back-to-back launches on an L2-resident matrix (reference protocol, src/dasp_f64.h:1301-1311)")),
+            "variant": args.variant, "threshold": 0.75, "block_longest": 256}
 
 
 def measured_peak_gbs():
@@ -174,21 +201,22 @@ def measured_peak_gbs():
 # ------------------------------------------------------------------------------------------------
 # reference arm: serial-CSR definition on host cores, bounded sample
 
-def host_sample(args, spec, target_nnz=60_000_000):
-    """First rows of the workload holding about target_nnz entries, as host CSR (float64)."""
+def host_csr(args, spec, target_nnz=None):
+    """The workload (or, with target_nnz, its first rows holding about that many entries) as host CSR in float64."""
     import torch
 
     from dasp_b200 import synth
 
     if torch.cuda.is_available():
         dev = torch.device("cuda:0")
-        ln = synth.row_lengths(spec, 0, spec.m, dev)
-        cs = torch.cumsum(ln, 0)
-        rows = int(torch.searchsorted(cs, torch.tensor([target_nnz], device=dev)).item()) + 1
-        rows = min(rows, spec.m)
-        del ln, cs
+        rows = int(spec.m)
+        if target_nnz is not None:
+            ln = synth.row_lengths(spec, 0, spec.m, dev)
+            cs = torch.cumsum(ln, 0)
+            rows = min(int(torch.searchsorted(cs, torch.tensor([target_nnz], device=dev)).item()) + 1, int(spec.m))
+            del ln, cs
         rp, ci, v, nnz = synth.generate(spec, 0, rows, dev)
-        out = (rows, spec.n, rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy())
+        out = (rows, int(spec.n), rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy())
         del rp, ci, v
         torch.cuda.empty_cache()
         return out
@@ -196,43 +224,51 @@ def host_sample(args, spec, target_nnz=60_000_000):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import matrices
 
-    m, n, rp, ci, v = matrices.stencil27(min(args.grid, 96))
-    return m, n, rp, ci, v
+    return matrices.stencil27(min(args.grid, 96))
 
 
-def cpu_leg(args, spec, threads, steps, warmup):
+def cpu_leg(args, spec, threads, steps, warmup, target_nnz):
+    """Serial CSR loop of oracle/ (per thread: contiguous row ranges) on host cores; every step is one full pass."""
     import oracle
 
-    m, n, rp, ci, v = host_sample(args, spec)
+    m, n, rp, ci, v = host_csr(args, spec, target_nnz)
     nnz = int(rp[m])
     x = np.random.default_rng(7).uniform(-1, 1, n)
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(warmup):
         oracle.csr_spmv_f64(m, rp, ci, v, x, threads=threads)
-    ts = []
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
         oracle.csr_spmv_f64(m, rp, ci, v, x, threads=threads)
-        ts.append(time.perf_counter() - t0)
-    t = float(np.mean(ts))
+    t = (time.perf_counter() - t0) / steps
+    whole = m == int(spec.m)
     return {"value": 2.0 * nnz / t / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
-            "sample": f"rows [0,{m}) of the workload ({nnz} nnz), serial CSR loop per thread, mean of {steps} passes",
-            "ms_per_step": t * 1e3,
+            "sample": (f"the whole workload ({m} rows, {nnz} nnz)" if whole else f"rows [0,{m}) of the workload ({nnz} nnz)")
+                      + f", serial CSR loop per thread, mean of {steps} passes after {warmup} warm-up passes",
+            "ms_per_step": t * 1e3, "m": m, "n": n, "nnz": nnz,
             "hbm_gbs": algorithmic_bytes(m, n, nnz, 8) / t / 1e9}
 
 
 def run_reference(args):
+    """--impl reference: the reference ships no CPU SpMV; its result is DEFINED by the serial CSR loop (oracle/), here
+    row-parallel over all host threads, on the WHOLE workload of our arm, K timed passes after W warm-up passes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     spec, wname, half = make_spec(args)
     threads = os.cpu_count() or 1
-    steps = max(3, min(args.steps, 10))
-    leg = cpu_leg(args, spec, threads, steps, args.warmup)
+    # C4 (5.4 GB of host CSR, ~40 ms per pass on 16 threads) and smaller run whole; the 1.1 G-entry C5 shapes are sampled
+    big = args.workload in ("c5", "c5_spec") and args.scale > 0.3
+    leg = cpu_leg(args, spec, threads, args.steps, args.warmup, 200_000_000 if big else None)
+    m, n, nnz = leg["m"], leg["n"], leg["nnz"]
+    b_alg_rank = algorithmic_bytes(m // world, n, nnz // world, 8)
+    cfg = config_dict(args, spec, wname, int(spec.m), int(spec.n), nnz, world, b_alg_rank, b_alg_rank < 256e6, args.cold)
     line = {
         "impl": "reference", "metric": "spmv_gflops", "value": leg["value"], "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": leg["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "note": "the reference ships no CPU SpMV; this is the serial CSR loop that defines its result (oracle/), row-parallel on all host threads"},
+        "config": cfg,
+        "note": "the reference ships no CPU SpMV; this is the serial CSR loop that defines its result (oracle/), row-parallel on all host threads",
         "hbm_gbs": leg["hbm_gbs"],
         "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": leg["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -285,17 +321,17 @@ def run_ours(args):
     h = dasp_b200.Dasp(dtype, r1 - r0, n, rp, ci, v, device=local, nnz=nnz)
     create_s = time.perf_counter() - t0
     st = h.stats()
-    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3, "tma": 4}[args.variant]
-    h.set_variant(0 if var == 4 else var, 0 if var == 3 else var, var if var == 2 else 0)
+    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3, "tma": 4, "blocked": 5}[args.variant]
+    h.set_variant(0 if var in (4, 5) else var, 0 if var == 3 else var, var if var == 2 else 0)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
     x = (torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdt)
     y = torch.zeros(max(r1 - r0, 1), dtype=tdt, device=dev)
 
-    # bounded parity check inside the bench: first rows of this slab against an independent float64 evaluation of the
-    # CSR definition on the device (the oracle itself is only used by tests/, smoke() and the CPU-baseline legs)
-    chk_rows = min(r1 - r0, 200000)
+    # parity check inside the bench: ALL rows of this slab against an independent float64 evaluation of the CSR
+    # definition on the device (the oracle itself is only used by tests/, smoke() and the CPU-baseline legs)
+    chk_rows = r1 - r0
     chk = None
     if chk_rows > 0:
         yy = torch.empty_like(y)
@@ -404,19 +440,18 @@ def run_ours(args):
 
     peak, peak_src = measured_peak_gbs()
     b_alg_total = algorithmic_bytes(m, n, nnz_total, esz)
-    b_alg_rank = algorithmic_bytes(r1 - r0, n, nnz, esz)
+    # per-rank algorithmic bytes: the slab's CSR, its y, and the part of x the slab READS (its column range), not the
+    # whole replicated x (a stencil slab reads 1/P of x plus a halo)
+    x_read = (st["col_max"] - st["col_min"] + 1) if st["col_max"] >= st["col_min"] else 0
+    b_alg_rank = algorithmic_bytes(r1 - r0, x_read, nnz, esz) if world > 1 else b_alg_total
     ach = b_alg_rank / (ms_local / args.steps * 1e-3) / 1e9
     line = {
         "metric": "spmv_gflops", "value": 2.0 * nnz_total / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16" if half else "f64", "data": "synthetic",
-        "config": {"workload": wname, "m": m, "n": n, "nnz": nnz_total, "seed": int(spec.seed),
-                   "partition": "nnz-balanced contiguous row slabs, x replicated" if world > 1 else "single GPU",
-                   "l2": ("L2 flushed before every launch" if flush is not None else
-                          ("inputs exceed L2 (%.0f MB per rank)" % (b_alg_rank / 1e6) if not small else
-                           "warm L2: back-to-back launches on an L2-resident matrix (reference protocol, src/dasp_f64.h:1301-1311)")),
-                   "variant": args.variant, "threshold": 0.75, "block_longest": 256},
+        "config": config_dict(args, spec, wname, m, n, nnz_total, world,
+                              algorithmic_bytes(m // world, n, nnz_total // world, 8), small, args.cold),
         "hbm_gbs": b_alg_total / (ms_step * 1e-3) / 1e9,
         "hbm_frac_of_8tbs": b_alg_total / (ms_step * 1e-3) / 8e12 / world,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -425,8 +460,8 @@ def run_ours(args):
         "gpu_launches": args.steps * h.launches_per_spmv(),
         "clocks": clk.summary(),
         "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
-                "h2d_bytes_per_step": n * esz, "d2h_bytes_per_step": (r1 - r0) * esz, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "path": "dasp_spmv_host_batch: every step uploads its x from pinned host memory, runs the fused kernel and downloads its y; independent steps pipelined over 3 streams (upload / kernel / download), per rank",
+                "h2d_bytes_per_step": x_read * esz, "d2h_bytes_per_step": (r1 - r0) * esz, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "path": "dasp_spmv_host_batch: every step uploads the part of its x this rank's slab reads (columns col_min..col_max) from pinned host memory, runs the fused kernel and downloads its y slab; independent steps pipelined over 3 streams (upload / kernel / download), per rank; bytes are rank 0's",
                 "one_blocking_call_per_step": {"value": 2.0 * nnz_total / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms,
                                                "path": "dasp_spmv_host (H2D, kernel, D2H back to back, synchronous)"}},
         "preprocess": {"gpu_ms": st["preprocess_ms"], "create_wall_s": create_s, "rate_fill0": st["rate_fill0"],
@@ -439,7 +474,7 @@ def run_ours(args):
 
     if world == 1 and not args.no_cpu and not half:
         try:
-            leg = cpu_leg(args, spec, 1, 3, 1)
+            leg = cpu_leg(args, spec, 1, 3, 1, 60_000_000)
             line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
         except Exception as e:  # the CPU leg must never take the GPU number down with it
@@ -472,6 +507,9 @@ def run_ours(args):
         except Exception as e:
             sec["ref_dasp_sm100a"] = {"error": repr(e)}
         line["secondary"] = sec
+        rk = sec.get("ref_dasp_sm100a", {})
+        line["vs_reference_kernels_sm100a"] = {k: {"speedup": e.get("speedup"), "ref_ms": e.get("ref_ms"), "ours_ms": e.get("ours_ms")}
+                                               for k, e in rk.items() if isinstance(e, dict) and "speedup" in e}
 
     h.close()
     if world == 1 and args.workload == "c4" and not args.no_others and not args.no_secondary:
@@ -647,8 +685,11 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
 
 def other_configs(args, dev):
     """Short measurements of the remaining BASELINE.json configurations (1 GPU), same protocol as the headline:
-    generate on the device, dasp_create, bounded parity check against an independent device-side evaluation, K back-to-back
-    launches timed with CUDA events from C."""
+    generate on the device, dasp_create, parity check of ALL rows against an independent device-side evaluation, K
+    back-to-back launches timed with CUDA events from C.  C3 and C5 are reported on BOTH generators: `c3_spec` / `c5_spec`
+    follow SURVEY.md 8(d) literally (unsorted columns; C5 long rows uniform over all n), `c3` / `c5` are the CSR-sorted
+    variants (ascending windowed columns; C5 long rows in a common 2^21 band).  The L2-resident C1 / C2 are reported warm
+    (reference protocol) AND cold (L2 flushed before every launch)."""
     import copy
 
     import torch
@@ -656,8 +697,9 @@ def other_configs(args, dev):
     import dasp_b200
     from dasp_b200 import synth
 
+    peak, _ = measured_peak_gbs()
     out = {}
-    for w in ("c1", "c2", "c3", "c5"):
+    for w in ("c1", "c2", "c3_spec", "c3", "c5_spec", "c5"):
         a = copy.copy(args)
         a.workload, a.scale = w, 1.0
         try:
@@ -667,27 +709,46 @@ def other_configs(args, dev):
             m, n = int(spec.m), int(spec.n)
             rp, ci, v, nnz = synth.generate(spec, 0, m, dev, half=half)
             h = dasp_b200.Dasp(dasp_b200.DASP_F16 if half else dasp_b200.DASP_F64, m, n, rp, ci, v, nnz=nnz)
+            st = h.stats()
             gen = torch.Generator(device=dev)
             gen.manual_seed(7)
             x = (torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdt)
             y = torch.zeros(m, dtype=tdt, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rows = min(m, 200000)
             h.spmv_unpermuted(x, y, stream)
             torch.cuda.synchronize(dev)
-            err = device_check(rp, ci, v, x, y, rows)
+            err = device_check(rp, ci, v, x, y, m)
             if err > (2e-3 if half else 1e-12):
                 raise RuntimeError(f"parity check failed: {err}")
             del rp, ci, v
             torch.cuda.empty_cache()
-            small = algorithmic_bytes(m, n, nnz, esz) < 256e6
+            b = algorithmic_bytes(m, n, nnz, esz)
+            small = b < 256e6
             steps, warm = (2000, 200) if small else (20, 5)
             ms = h.spmv_timed(x, y, stream, warm, steps) / steps
-            b = algorithmic_bytes(m, n, nnz, esz)
+
+            def entry(ms, l2):
+                return {"ms_per_step": ms, "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "hbm_gbs": b / (ms * 1e-3) / 1e9,
+                        "hbm_frac_of_8tbs": b / (ms * 1e-3) / 8e12, "roofline_frac_of_measured_peak": b / (ms * 1e-3) / 1e9 / peak,
+                        "l2": l2}
+
             out[w] = {"workload": wname, "m": m, "nnz": nnz, "dtype": "f16" if half else "f64", "steps": steps,
-                      "ms_per_step": ms, "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "hbm_gbs": b / (ms * 1e-3) / 1e9,
-                      "hbm_frac_of_8tbs": b / (ms * 1e-3) / 8e12, "parity_check_rel_l2": err,
-                      "l2": "warm L2, back-to-back launches (reference protocol)" if small else "inputs exceed L2"}
+                      "parity_check_rel_l2_all_rows": err, "launches_per_spmv": h.launches_per_spmv(),
+                      "preprocess_gpu_ms": st["preprocess_ms"]}
+            out[w].update(entry(ms, "warm L2, back-to-back launches (reference protocol)" if small else "inputs exceed L2"))
+            if small:  # cold: L2 flushed (512 MB written) before every timed launch
+                flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+                tot, k = 0.0, 200
+                for _ in range(k):
+                    synth.flush_l2(flush)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    h.spmv(x, y, stream)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                    tot += e0.elapsed_time(e1)
+                out[w]["cold"] = entry(tot / k, "L2 flushed before every launch, one launch per event pair")
+                del flush
             h.close()
             del x, y
             torch.cuda.empty_cache()
@@ -711,9 +772,12 @@ def reference_kernels_leg(args, dev):
         return {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
     out = {}
     g = min(args.grid, 128)
-    samples = [("stencil", synth.stencil27(g), False, f"27-point stencil {g}^3 fp64"),
-               ("c1", synth.banded(), False, "cop20k_A stand-in fp64"),
-               ("c2", synth.banded(), True, "cop20k_A stand-in fp16")]
+    samples = [("stencil", synth.stencil27(g), False, f"27-point stencil {g}^3 fp64")]
+    if args.grid > 128 and args.workload == "c4":  # the headline shape itself: ~7 s of single-threaded reference preprocessing
+        samples.append(("c4", synth.stencil27(args.grid), False, f"27-point stencil {args.grid}^3 fp64 (C4)"))
+    samples += [
+("c1", synth.banded(), False, "cop20k_A stand-in fp64"),
+                ("c2", synth.banded(), True, "cop20k_A stand-in fp16")]
     s = torch.cuda.current_stream(dev).cuda_stream
     for key, spec, half, label in samples:
         try:

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 DASP_F64, DASP_F16 = 0, 1
-VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA = 0, 1, 2, 3, 4
+VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA, VARIANT_BLOCKED = 0, 1, 2, 3, 4, 5
 
 _STATS_INT = [
     "dtype", "m", "n", "nnz",  # nnz is int64, handled below
@@ -29,6 +29,10 @@ class _Stats(C.Structure):
                 + [("rate_fill0", C.c_double), ("data_X", C.c_int64), ("data_X2", C.c_int64),
                    ("data_origin1", C.c_int64), ("preprocess_ms", C.c_double), ("device_bytes", C.c_int64),
                    ("col_min", C.c_int), ("col_max", C.c_int)])
+
+
+def stats_struct_size() -> int:
+    return C.sizeof(_Stats)
 
 
 ARRAYS = ["order_rid", "long_rpt_new", "long_val", "long_cid", "blockPtr", "irreg_rpt", "irreg_val",

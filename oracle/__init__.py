@@ -97,9 +97,23 @@ def _canon(dtype, rowptr, colidx, val):
     return rowptr, colidx, val
 
 
+class _Owned:
+    """Keeps the C layout alive while views into its arrays exist (preprocess(copy=False))."""
+
+    def __init__(self, lay):
+        self.lay = lay
+
+    def __del__(self):
+        try:
+            lib().dasp_oracle_free(C.byref(self.lay))
+        except Exception:
+            pass
+
+
 def preprocess(dtype: int, m: int, n: int, rowptr, colidx, val, threshold: float = 0.75,
-               block_longest: int = 256) -> dict:
-    """Run the C restatement; returns {scalar: int, array: np.ndarray (copies)}."""
+               block_longest: int = 256, copy: bool = True) -> dict:
+    """Run the C restatement; returns {scalar: int, array: np.ndarray}.  copy=False returns views into the C buffers
+    (full-size configurations: no second copy of a 14 GB layout); they stay valid as long as the dict lives."""
     rowptr, colidx, val = _canon(dtype, rowptr, colidx, val)
     nnz = int(rowptr[m])
     lay = _Layout()
@@ -115,8 +129,12 @@ def preprocess(dtype: int, m: int, n: int, rowptr, colidx, val, threshold: float
             out[a] = np.zeros(0, dtype=npdt)
         else:
             buf = (C.c_char * (cnt * np.dtype(npdt).itemsize)).from_address(ptr)
-            out[a] = np.frombuffer(buf, dtype=npdt).copy()
-    lib().dasp_oracle_free(C.byref(lay))
+            view = np.frombuffer(buf, dtype=npdt)
+            out[a] = view.copy() if copy else view
+    if copy:
+        lib().dasp_oracle_free(C.byref(lay))
+    else:
+        out["_owner"] = _Owned(lay)
     return out
 
 

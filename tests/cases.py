@@ -76,6 +76,7 @@ CASES = {
     "wide_span_mixed": lambda: _wide_mixed(),
     "rowloop_59989": lambda: _lens([5] * 59989 + [1, 2, 3], n=70000, seed=8, window=64),
     "rowloop_59990": lambda: _lens([5] * 59990 + [1, 2, 3], n=70000, seed=8, window=64),
+    "rowloop_399999": lambda: _lens([6] * 399999, n=400000, seed=9, window=64),
     "rowloop_400000": lambda: _lens([6] * 400000, n=400000, seed=9, window=64),
 }
 
@@ -90,7 +91,7 @@ def get(name):
 
 
 # cheap subset for the no-GPU suite (the big rowloop cases only matter for array lengths)
-CPU_CASES = [k for k in CASES if k not in ("rowloop_400000",)]
+CPU_CASES = [k for k in CASES if k not in ("rowloop_400000", "rowloop_399999")]
 
 
 def x_for(n, seed=7):

@@ -28,7 +28,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["nnz"] > 0 and d["config"]["m"] == d["config"]["n"] == 24 ** 3
+    assert d["steps"] == 3 and d["warmup"] == 1  # the flags are honoured, and every step is one pass over the whole workload
+    assert "whole workload" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -66,10 +66,10 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         order = ref["order_rid"]
         tdt = torch.float16 if dtype == oracle.F16 else torch.float64
         dx = torch.from_numpy(x).to(cuda_device)
-        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA]
-                        if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA]):
-            # medium: cuda/mma/split; long: cuda/mma/tma; short: cuda/mma (a variant that does not apply = cuda-core)
-            h.set_variant(variant if variant != dasp.VARIANT_TMA else dasp.VARIANT_CUDA_CORE,
+        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED]
+                        if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED]):
+            # medium: cuda/mma/split; long: cuda/mma/tma/blocked; short: cuda/mma (a variant that does not apply = cuda-core)
+            h.set_variant(variant if variant not in (dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED) else dasp.VARIANT_CUDA_CORE,
                           variant if variant != dasp.VARIANT_SPLIT else dasp.VARIANT_CUDA_CORE,
                           variant if variant == dasp.VARIANT_MMA else dasp.VARIANT_AUTO)
             for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
@@ -91,7 +91,7 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
                 torch.cuda.synchronize()
                 h.set_index_compression(True)
                 assert bool(torch.equal(dy2, dy)), f"{name}: compact indices change the result"
-            # original-order output
+            # original-order output (the last variant of the loop is still selected: the blocked long rows)
             dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
             h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
@@ -135,6 +135,111 @@ def test_device_csr_input(dasp, cuda_device):
     for a in dasp.lib.ARRAYS:
         assert np.array_equal(h.export(a).view(np.uint8), ref[a].view(np.uint8)), a
     h.close()
+
+
+def test_malformed_csr_is_rejected(dasp, cuda_device):
+    """dasp_create validates the CSR on the device: rowptr[0] != 0, decreasing rowptr, rowptr[m] != nnz and columns outside
+    [0, n) all fail with a status instead of indexing out of bounds."""
+    m, n, rp, ci, v = get("mixed_f1")
+    nnz = int(rp[m])
+    bad = []
+    r = rp.copy(); r[0] = 1; bad.append((r, ci, nnz))
+    r = rp.copy(); r[5], r[6] = r[6] + 3, r[5]; bad.append((r, ci, nnz))
+    bad.append((rp, ci, nnz - 1))
+    c = ci.copy(); c[nnz // 2] = n; bad.append((rp, c, nnz))
+    c = ci.copy(); c[7] = -1; bad.append((rp, c, nnz))
+    for r, c, k in bad:
+        with pytest.raises(dasp.DaspError, match="malformed CSR"):
+            dasp.Dasp(oracle.F64, m, n, r, c, v, nnz=k)
+    h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)  # and the library is still usable afterwards
+    st = h.stats()
+    assert (st["col_min"], st["col_max"]) == (int(ci.min()), int(ci.max()))
+    h.close()
+
+
+def test_host_path_uploads_only_the_column_range(dasp, cuda_device):
+    """A row slab whose columns lie in [col_min, col_max]: dasp_spmv_host must not read x outside that range (the rest of
+    the host vector is poisoned with NaN) and still give the CSR result."""
+    m, n, rp, ci, v = get("stencil27_12")
+    r0, r1 = m // 3, 2 * m // 3
+    rps = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+    cis, vs = ci[rp[r0]:rp[r1]], v[rp[r0]:rp[r1]]
+    h = dasp.Dasp(oracle.F64, r1 - r0, n, rps, cis, vs)
+    st = h.stats()
+    assert st["col_min"] == int(cis.min()) and st["col_max"] == int(cis.max()) and st["col_max"] - st["col_min"] + 1 < n
+    x = x_for(n)
+    xp = np.full(n, np.nan)
+    xp[st["col_min"]:st["col_max"] + 1] = x[st["col_min"]:st["col_max"] + 1]
+    y = h.spmv_host(xp)
+    ref = oracle.csr_spmv_f64(r1 - r0, rps, cis, vs, x)
+    assert _rel_l2(y, ref[h.export("order_rid")]) <= FP64_TOL
+    h.close()
+
+
+def test_corrupted_checkpoint_is_rejected(dasp, cuda_device, tmp_path):
+    """dasp_load checks the file against more than itself: format version, consistent scalars, monotone offsets, indices in
+    range, no trailing bytes."""
+    import struct
+
+    m, n, rp, ci, v = get("mixed_f1")
+    h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)
+    path = str(tmp_path / "a.dasp")
+    h.save(path)
+    st = h.stats()
+    h.close()
+    good = open(path, "rb").read()
+
+    def load(data):
+        q = str(tmp_path / "b.dasp")
+        open(q, "wb").write(data)
+        return dasp.Dasp.load_file(q)
+
+    load(good).close()
+    with pytest.raises(dasp.DaspError):  # trailing bytes
+        load(good + b"\0")
+    with pytest.raises(dasp.DaspError):  # truncated
+        load(good[:-16])
+    with pytest.raises(dasp.DaspError):  # wrong version
+        load(good[:8 + 16] + struct.pack("<i", 99) + good[8 + 20:])
+    # first array of the file is order_rid: make it a non-permutation
+    head = 8 + 24 + 8 + dasp.lib.stats_struct_size()
+    assert struct.unpack_from("<q", good, head)[0] == 4 * m
+    data = bytearray(good)
+    struct.pack_into("<i", data, head + 8, struct.unpack_from("<i", good, head + 12)[0])
+    with pytest.raises(dasp.DaspError):
+        load(bytes(data))
+    # a column index out of range in long_cid (4th array)
+    off = head
+    for k in range(3):
+        off += 8 + struct.unpack_from("<q", good, off)[0]
+    assert struct.unpack_from("<q", good, off)[0] == 4 * st["fill0_nnz_long"]
+    data = bytearray(good)
+    struct.pack_into("<i", data, off + 8, n + 5)
+    with pytest.raises(dasp.DaspError):
+        load(bytes(data))
+
+
+def test_two_handles_keep_their_devices(dasp, cuda_device):
+    """Every entry selects the handle's device itself and restores the caller's; with two GPUs visible a handle on device 1
+    is created and used while device 0 stays current (skipped on a single-GPU box, where only the restore is checked)."""
+    import torch
+
+    m, n, rp, ci, v = get("mixed_f1")
+    x = x_for(n)
+    ref = oracle.csr_spmv_f64(m, rp, ci, v, x)
+    ndev = torch.cuda.device_count()
+    torch.cuda.set_device(0)
+    handles = [dasp.Dasp(oracle.F64, m, n, rp, ci, v, device=d) for d in range(min(ndev, 2))]
+    assert torch.cuda.current_device() == 0
+    for d, h in enumerate(handles):
+        dx = torch.from_numpy(x).to(f"cuda:{d}")
+        dy = torch.zeros(m, dtype=torch.float64, device=f"cuda:{d}")
+        h.spmv(dx, dy, 0)  # default stream of the handle's device, while device 0 is current
+        torch.cuda.synchronize(d)
+        assert torch.cuda.current_device() == 0
+        assert _rel_l2(dy.cpu().numpy(), ref[h.export("order_rid")]) <= FP64_TOL
+    for h in handles:
+        h.close()
 
 
 def test_bad_arguments_fail_loudly(dasp, cuda_device):
@@ -181,6 +286,7 @@ def test_axpby_and_checkpoint_roundtrip(dasp, cuda_device, dtype, tmp_path):
     f = oracle.csr_spmv_f16 if dtype == oracle.F16 else oracle.csr_spmv_f64
     ax = f(m, rp, ci, v, x)
     h = dasp.Dasp(dtype, m, n, rp, ci, v)
+    h.set_variant(0, dasp.VARIANT_CUDA_CORE, 0)  # bit equality below: the chunked long rows merge deterministically
     order = h.export("order_rid")
     s = torch.cuda.current_stream().cuda_stream
     dx = torch.from_numpy(x).to(cuda_device)
@@ -196,6 +302,7 @@ def test_axpby_and_checkpoint_roundtrip(dasp, cuda_device, dtype, tmp_path):
     path = str(tmp_path / "layout.dasp")
     h.save(path)
     h2 = dasp.Dasp.load_file(path)
+    h2.set_variant(0, dasp.VARIANT_CUDA_CORE, 0)
     assert (h2.m, h2.n, h2.nnz, h2.dtype) == (m, n, int(rp[m]), dtype)
     for a in dasp.lib.ARRAYS:
         assert np.array_equal(h.export(a).view(np.uint8), h2.export(a).view(np.uint8)), a
@@ -248,6 +355,7 @@ def test_host_batch_equals_individual_products(dasp, cuda_device, dtype):
     m, n, rp, ci, v = get("powerlaw_20k")
     tdt = torch.float16 if dtype == oracle.F16 else torch.float64
     h = dasp.Dasp(dtype, m, n, rp, ci, v.astype(np.float16 if dtype == oracle.F16 else np.float64))
+    h.set_variant(0, dasp.VARIANT_CUDA_CORE, 0)  # bit equality below
     for count in (1, 2, 5):
         xs = [torch.from_numpy(x_for(n, seed=100 + j)).to(tdt).pin_memory() for j in range(count)]
         ys = [torch.full((m,), float("nan"), dtype=tdt).pin_memory() for _ in range(count)]
@@ -267,6 +375,7 @@ def test_spmv_is_cuda_graph_capturable(dasp, cuda_device):
 
     m, n, rp, ci, v = get("mixed_f1")
     h = dasp.Dasp(oracle.F64, m, n, rp, ci, v)
+    h.set_variant(0, dasp.VARIANT_CUDA_CORE, 0)  # bit equality below
     dx = torch.from_numpy(x_for(n)).to(cuda_device)
     y_direct = torch.zeros(m, dtype=torch.float64, device=cuda_device)
     y_graph = torch.zeros(m, dtype=torch.float64, device=cuda_device)

@@ -85,3 +85,62 @@ def test_product_on_generated_matrices(cuda_device, kind, half):
     err = np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref)
     assert err <= (2e-3 if half else 1e-12)
     h.close()
+
+
+@pytest.mark.parametrize("kind", ["powerlaw_spec", "skewed_spec"])
+def test_spec_literal_generators(cuda_device, kind):
+    """Kinds 4 / 5 (SURVEY.md §8(d) taken literally): slabs concatenate to the global matrix, columns are in range, DISTINCT
+    within every row and NOT sorted; C3: 9 of 10 entries inside the row's window; C5: exactly n_long long rows at one seeded
+    position per stride, their columns spread over all of n; and the product on them matches the oracle."""
+    import torch
+
+    import dasp_b200
+    from dasp_b200 import synth
+
+    spec = {"powerlaw_spec": lambda: synth.powerlaw_spec(m=60000, lmax=20000, window=512),
+            "skewed_spec": lambda: synth.skewed_spec(n_long=7, long_len=9000, n_short=40000, window=512)}[kind]()
+    m, n = int(spec.m), int(spec.n)
+    rp, ci, v, nnz = _host(spec, 0, m, cuda_device)
+    cut = m // 3
+    a, b = _host(spec, 0, cut, cuda_device), _host(spec, cut, m, cuda_device)
+    assert a[3] + b[3] == nnz and np.array_equal(np.concatenate([a[1], b[1]]), ci) and np.array_equal(np.concatenate([a[2], b[2]]), v)
+    assert ci.min() >= 0 and ci.max() < n
+    lens = np.diff(rp)
+    rows = np.repeat(np.arange(m), lens)
+    key = rows.astype(np.int64) * n + ci
+    assert len(np.unique(key)) == nnz, "duplicate column inside a row"
+    longest = int(np.argmax(lens))
+    c = ci[rp[longest]:rp[longest + 1]]
+    assert np.any(np.diff(c) < 0), "columns of the longest row are sorted"
+    if kind == "skewed_spec":
+        long_rows = np.flatnonzero(lens == 9000)
+        stride = m // 7
+        assert len(long_rows) == 7 and np.array_equal(long_rows // stride, np.arange(7))
+        assert set(np.unique(lens[lens != 9000])) <= {1, 2, 3, 4}
+        assert c.max() - c.min() > n // 2
+        short = np.flatnonzero(lens <= 4)[:2000]
+        for r in short[::97]:
+            cc = ci[rp[r]:rp[r + 1]]
+            assert np.all(np.abs(cc - r * n / m) <= 2 * 512)
+    else:
+        assert lens.max() > 1000 and np.median(lens) <= 2
+        r = int(np.flatnonzero((lens >= 50) & (lens < 400))[0])
+        cc = ci[rp[r]:rp[r + 1]]
+        inside = np.abs(cc - r * n / m) <= 512 + 1
+        assert 0.85 <= inside.mean() <= 0.95
+    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, n, rp, ci, v)
+    ref = oracle.preprocess(oracle.F64, m, n, rp, ci, v)
+    for arr in dasp_b200.lib.ARRAYS:
+        assert np.array_equal(h.export(arr).view(np.uint8), ref[arr].view(np.uint8)), arr
+    x = np.random.default_rng(1).uniform(-1, 1, n)
+    dx = torch.from_numpy(x).to(cuda_device)
+    y_ref = oracle.csr_spmv_f64(m, rp, ci, v, x)[ref["order_rid"]]
+    for long_variant in (dasp_b200.VARIANT_CUDA_CORE, dasp_b200.VARIANT_BLOCKED):
+        h.set_variant(0, long_variant, 0)
+        for rep in range(2):
+            dy = torch.full((m,), float("nan"), dtype=torch.float64, device=cuda_device)
+            h.spmv(dx, dy, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            y = dy.cpu().numpy()
+            assert np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref) <= 1e-12, (long_variant, rep)
+    h.close()
