@@ -98,6 +98,7 @@ struct Layout {
     int *reg_cbase = nullptr;              // [fill0_nnz_reg / 32]
     unsigned short *reg_cdelta = nullptr;  // [fill0_nnz_reg]
     unsigned char *blk_wide = nullptr;     // [blocknum] 1: some tile of the block spans >= 65535 columns -> use reg_cid
+    unsigned short *blk_live = nullptr;    // [blocknum] tiles of the block up to the last one holding a non-zero value
     int *long_cbase = nullptr;              // [fill0_nnz_long / 32] same compact form for the long part
     unsigned short *long_cdelta = nullptr;  // [fill0_nnz_long]
     unsigned char *long_wide = nullptr;     // [n_long_units] in execution order
@@ -109,12 +110,11 @@ struct Layout {
     // TMA bulk copy and gathers from there.  12 (f64) / 6 (f16) bytes per entry like the CSR itself.
     int lcb_bw_log2 = 0;                    // block width = 1 << lcb_bw_log2 columns
     int lcb_nblk = 0;                       // column blocks
-    int lcb_live = 0;                       // entries (padding dropped)
+    int lcb_live = 0;                       // entries (reference padding dropped, every block padded to a multiple of 4)
     int lcb_nctas = 0;                      // CTAs of the LCB kernel (LCB_PART entries each, never across blocks)
     void *lcb_val = nullptr;                // [lcb_live]
-    unsigned short *lcb_col = nullptr;      // [lcb_live] column - block * width
-    unsigned short *lcb_row = nullptr;      // [lcb_live] long-row index (row_long <= 65535)
-    int *lcb_blk_ptr = nullptr;             // [lcb_nblk + 1] first entry of each block
+    unsigned *lcb_idx = nullptr;            // [lcb_live] long-row index << 16 | column - block * width (row_long <= 65535)
+    int *lcb_blk_ptr = nullptr;             // [lcb_nblk + 1] first entry of each block (multiples of 4)
     int *lcb_cta_first = nullptr;           // [lcb_nblk + 1] first CTA of each block
     void *lcb_acc = nullptr;                // [row_long] accumulators (double / float), zero between launches
     unsigned *lcb_done = nullptr;           // [1] CTAs finished in the current launch (self-resetting)
@@ -134,6 +134,7 @@ struct dasp_handle {
     int category_mask = 15;
     int index_compression = 1;
     int sm_count = 0;
+    const void *carved_narrow = nullptr; // the same for the 128-thread small-matrix kernels
     const void *carved_kernel = nullptr; // kernel whose L1 carve-out preference was already set on this device
     dasp_variant var_medium = DASP_VARIANT_AUTO, var_long = DASP_VARIANT_AUTO, var_short = DASP_VARIANT_AUTO;
     // device staging of x / y for dasp_spmv_host (owned by pool)
@@ -148,7 +149,7 @@ struct dasp_handle {
 
 namespace dasp {
 constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
-constexpr int LCB_PART = 16384;     // entries per CTA of the column-blocked long-row kernel
+constexpr int LCB_PART = 32768;     // entries per CTA of the column-blocked long-row kernel (a multiple of 8 warps x 128)
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
 
 // preprocess.cu

@@ -65,15 +65,20 @@ __global__ void flag_irreg(const int *__restrict__ irreg_rpt, int row_block, int
 // column is the base and every slot stores (column - base) in 16 bits.  Column 0 (all padding slots, and genuine
 // entries of column 0) is the sentinel 0xFFFF, so the kernels gather exactly the x entries the reference layout
 // names.  A block with a tile spanning >= 65535 columns is flagged wide and keeps using reg_cid.
-__global__ void compress_cid(const int *__restrict__ blockPtr, const int *__restrict__ reg_cid, int blocknum,
-                             int *__restrict__ cbase, unsigned short *__restrict__ cdelta, unsigned char *__restrict__ wide)
+template <typename T>
+__global__ void compress_cid(const int *__restrict__ blockPtr, const int *__restrict__ reg_cid, const T *__restrict__ reg_val,
+                             int blocknum, int *__restrict__ cbase, unsigned short *__restrict__ cdelta,
+                             unsigned char *__restrict__ wide, unsigned short *__restrict__ live)
 {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= blocknum) return;
     const int lane = threadIdx.x & 31;
     const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
     bool any_wide = false;
+    int nlive = 0; // tiles up to the last one that holds a non-zero value: the kernels stop there (the FP16 layout pads
+                   // every block to a multiple of 4 tiles, src/dasp_f16.h:1356; a tile of zeros contributes nothing)
     for (int p = bp0; p < bp1; p += 32) {
+        if (__any_sync(0xffffffffu, reg_val[p + lane] != T(0))) nlive = ((p - bp0) >> 5) + 1;
         const int c = reg_cid[p + lane];
         int mn = c ? c : INT32_MAX, mx = c;
         for (int o = 16; o; o >>= 1) {
@@ -86,7 +91,7 @@ __global__ void compress_cid(const int *__restrict__ blockPtr, const int *__rest
         cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
         if (lane == 0) cbase[p >> 5] = mn;
     }
-    if (lane == 0) wide[b] = any_wide ? 1 : 0;
+    if (lane == 0) { wide[b] = any_wide ? 1 : 0; live[b] = (unsigned short)min(nlive, 65535); }
 }
 
 // The same compact index form for the long part: one warp per work unit (execution order), one base per 32-slot
@@ -160,24 +165,35 @@ __global__ void lcb_block_ptr(const int *__restrict__ sorted_key, int slots, int
     blk_ptr[b] = lo;
 }
 
-__global__ void lcb_ctas_per_block(const int *__restrict__ blk_ptr, int nblk, int *__restrict__ cta_first)
+// padded entry count of every block: a multiple of 4 (one 256-bit value load + one 128-bit index load per lane)
+__global__ void lcb_padded_counts(const int *__restrict__ blk_ptr, int nblk, int *__restrict__ pad_ptr, int *__restrict__ cta_first)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nblk) return;
-    cta_first[b] = b < nblk ? (blk_ptr[b + 1] - blk_ptr[b] + LCB_PART - 1) / LCB_PART : 0;
+    const int cnt = b < nblk ? ((blk_ptr[b + 1] - blk_ptr[b] + 3) & ~3) : 0;
+    pad_ptr[b] = cnt;
+    cta_first[b] = (cnt + LCB_PART - 1) / LCB_PART;
 }
 
+// entry i of the padded, blocked sequence: value, and (long row << 16 | column inside the block); pad entries repeat the
+// row of the last real entry of their block with value 0 and column 0
 template <typename T>
 __global__ void lcb_gather(const T *__restrict__ long_val, const int *__restrict__ long_cid, const int *__restrict__ src,
-                           const int *__restrict__ warp_row, int live, int longw, int bw_mask, T *__restrict__ val,
-                           unsigned short *__restrict__ col, unsigned short *__restrict__ row)
+                           const int *__restrict__ warp_row, const int *__restrict__ blk_ptr, const int *__restrict__ pad_ptr,
+                           int nblk, int total, int longw, int bw_mask, T *__restrict__ val, unsigned *__restrict__ idx)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= live) return;
-    const int p = src[i];
-    val[i] = long_val[p];
-    col[i] = (unsigned short)(long_cid[p] & bw_mask);
-    row[i] = (unsigned short)warp_row[p / longw];
+    if (i >= total) return;
+    int lo = 0, hi = nblk; // last block b with pad_ptr[b] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pad_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int b = lo, j = i - pad_ptr[b], cnt = blk_ptr[b + 1] - blk_ptr[b];
+    const int p = src[blk_ptr[b] + min(j, cnt - 1)];
+    const unsigned row = (unsigned)warp_row[p / longw];
+    if (j < cnt) { val[i] = long_val[p]; idx[i] = (row << 16) | (unsigned)(long_cid[p] & bw_mask); }
+    else { val[i] = T(0); idx[i] = row << 16; }
 }
 
 template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
@@ -192,12 +208,13 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     int bw_log2 = 0;
     while ((sizeof(T) << (bw_log2 + 1)) <= (size_t)LCB_BYTES) bw_log2++; // 8192 doubles / 32768 halves
     const int nblk = s.n > 0 ? (int)((((int64_t)s.n - 1) >> bw_log2) + 1) : 1;
-    int *warp_row = nullptr, *key = nullptr, *idx = nullptr, *skey = nullptr, *sidx = nullptr;
+    int *warp_row = nullptr, *key = nullptr, *idx = nullptr, *skey = nullptr, *sidx = nullptr, *blk_ptr = nullptr;
     DASP_TRY(tmp.alloc((void **)&warp_row, sizeof(int) * (size_t)s.warp_number));
     DASP_TRY(tmp.alloc((void **)&key, sizeof(int) * (size_t)slots));
     DASP_TRY(tmp.alloc((void **)&idx, sizeof(int) * (size_t)slots));
     DASP_TRY(tmp.alloc((void **)&skey, sizeof(int) * (size_t)slots));
     DASP_TRY(tmp.alloc((void **)&sidx, sizeof(int) * (size_t)slots));
+    DASP_TRY(tmp.alloc((void **)&blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
     DASP_CUDA(cudaMemsetAsync(warp_row, 0, sizeof(int) * (size_t)s.warp_number, st));
     lcb_warp_rows<<<s.row_long, 256, 0, st>>>(L.long_rpt_new, s.row_long, warp_row);
     lcb_keys<T><<<grid_for(slots, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, slots, bw_log2, nblk, key, idx);
@@ -206,27 +223,28 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     DASP_TRY(radix_sort_pairs(tmp, key, idx, skey, sidx, slots, bits, false, st));
     DASP_TRY(pool.alloc((void **)&L.lcb_blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
     DASP_TRY(pool.alloc((void **)&L.lcb_cta_first, sizeof(int) * (size_t)(nblk + 1)));
-    lcb_block_ptr<<<grid_for(nblk + 1, 256), 256, 0, st>>>(skey, slots, nblk, L.lcb_blk_ptr);
-    lcb_ctas_per_block<<<grid_for(nblk + 1, 256), 256, 0, st>>>(L.lcb_blk_ptr, nblk, L.lcb_cta_first);
+    lcb_block_ptr<<<grid_for(nblk + 1, 256), 256, 0, st>>>(skey, slots, nblk, blk_ptr);
+    lcb_padded_counts<<<grid_for(nblk + 1, 256), 256, 0, st>>>(blk_ptr, nblk, L.lcb_blk_ptr, L.lcb_cta_first);
+    DASP_TRY(scan_inplace(tmp, L.lcb_blk_ptr, nblk + 1, st));
     DASP_TRY(scan_inplace(tmp, L.lcb_cta_first, nblk + 1, st));
     int tot[2] = {0, 0};
     DASP_CUDA(cudaMemcpyAsync(&tot[0], L.lcb_blk_ptr + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaMemcpyAsync(&tot[1], L.lcb_cta_first + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
     DASP_CUDA(cudaStreamSynchronize(st));
-    const int live = tot[0];
-    DASP_TRY(pool.alloc(&L.lcb_val, sizeof(T) * (size_t)live));
-    DASP_TRY(pool.alloc((void **)&L.lcb_col, sizeof(unsigned short) * (size_t)live));
-    DASP_TRY(pool.alloc((void **)&L.lcb_row, sizeof(unsigned short) * (size_t)live));
+    const int total = tot[0];
+    if (total < 0) { set_error("column-blocked long part exceeds 32-bit offsets"); return DASP_ERR_RANGE; }
+    DASP_TRY(pool.alloc(&L.lcb_val, sizeof(T) * (size_t)total));
+    DASP_TRY(pool.alloc((void **)&L.lcb_idx, sizeof(unsigned) * (size_t)total));
     DASP_TRY(pool.alloc(&L.lcb_acc, 8 * (size_t)s.row_long));
     DASP_TRY(pool.alloc((void **)&L.lcb_done, sizeof(unsigned) * 4));
     DASP_CUDA(cudaMemsetAsync(L.lcb_acc, 0, 8 * (size_t)s.row_long, st));
     DASP_CUDA(cudaMemsetAsync(L.lcb_done, 0, sizeof(unsigned) * 4, st));
-    if (live > 0)
-        lcb_gather<T><<<grid_for(live, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, sidx, warp_row, live, longw,
-                                                          (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_col, L.lcb_row);
+    if (total > 0)
+        lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
+                                                           nblk, total, longw, (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_idx);
     DASP_CUDA(cudaGetLastError());
     DASP_CUDA(cudaStreamSynchronize(st)); // the scratch is released by the guard
-    L.lcb_bw_log2 = bw_log2; L.lcb_nblk = nblk; L.lcb_live = live; L.lcb_nctas = tot[1];
+    L.lcb_bw_log2 = bw_log2; L.lcb_nblk = nblk; L.lcb_live = total; L.lcb_nctas = tot[1];
     return DASP_OK;
 }
 
@@ -354,10 +372,16 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
     DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
     DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
+    DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
     if (cm > 0) flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
-    if (blocknum > 0)
-        compress_cid<<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(L.blockPtr, L.reg_cid, blocknum, L.reg_cbase,
-                                                                          L.reg_cdelta, L.blk_wide);
+    if (blocknum > 0) {
+        if (h->dtype == DASP_F16)
+            compress_cid<unsigned short><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
+                L.blockPtr, L.reg_cid, (const unsigned short *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
+        else
+            compress_cid<double><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
+                L.blockPtr, L.reg_cid, (const double *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
+    }
     // ---- inverse permutation (dasp_unpermute_to, relabelled mode) ----
     DASP_TRY(pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
     if (m > 0) invert_order<<<grid_for(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
@@ -367,16 +391,20 @@ int derive(dasp_handle *h, cudaStream_t st)
     // 32-lane gather of the chunked kernel touches (estimated from the column span of every 32-slot group) ----
     L.long_lines_avg = 0.0;
     h->lcb_auto = 0;
+    L.s.long_gather_lines = 0.0;
+    L.s.long_blocked = 0;
     if (cl > 0 && s.fill0_nnz_long > 0) {
         unsigned long long nl = 0;
         DASP_CUDA(cudaMemcpyAsync(&nl, lines, sizeof(nl), cudaMemcpyDeviceToHost, st));
         DASP_CUDA(cudaStreamSynchronize(st));
         L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
+        L.s.long_gather_lines = L.long_lines_avg;
         double thr = 12.0; // measured crossover, profiles/r02/README.md
         if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
         if (L.long_lines_avg > thr && cl <= 65535 && s.nnz_long >= 4 * LCB_PART) {
             DASP_TRY(build_lcb(h, st));
             h->lcb_auto = L.lcb_nctas > 0;
+            L.s.long_blocked = h->lcb_auto;
         }
     }
     DASP_CUDA(cudaStreamSynchronize(st));

@@ -22,6 +22,7 @@
 //
 // y is produced in permuted order (K11); with `scatter` (= order_rid) it is written to original order.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -71,6 +72,7 @@ struct SpmvArgs {
     const int *reg_cbase;             // compact indices: per-tile base
     const unsigned short *reg_cdelta; //                  per-slot 16-bit offset, 0xFFFF = column 0
     const unsigned char *blk_wide;    // nullptr: compression off; else 1 = block reads reg_cid
+    const unsigned short *blk_live;   // tiles of the block worth reading (trailing all-zero tiles dropped)
     int row_long, row_block, blocknum;
     // short
     const void *short_val;
@@ -82,7 +84,7 @@ struct SpmvArgs {
     int row_zero;
     // column-blocked long rows (LCB, derive.cu)
     const void *lcb_val;
-    const unsigned short *lcb_col, *lcb_row;
+    const unsigned *lcb_idx; // long row << 16 | column inside the block
     const int *lcb_blk_ptr, *lcb_cta_first;
     void *lcb_acc;
     unsigned *lcb_done;
@@ -455,7 +457,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
         const T *pv = val + bp0 + 4 * r;
         const int *pc = a.reg_cid + bp0 + 4 * r;
         const T *iv = static_cast<const T *>(a.irreg_val);
-        const int nt = (bp1 - bp0) >> 5;
+        const int nt = min((bp1 - bp0) >> 5, (int)__ldg(a.blk_live + b));
         // column indices of tile k: compact form (tile base + 16-bit offsets) unless a block of this warp is flagged
         // wide (warp-uniform choice: no divergence, one code path live at a time)
         const bool compact = __all_sync(0xffffffffu, a.blk_wide != nullptr && a.blk_wide[b] == 0);
@@ -801,8 +803,11 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
 }
 
 // One warp per work item; the block index selects the category (grid = sum of the per-category CTA counts).
-template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false>
-__global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
+// NT = threads per CTA: 256 for the bandwidth-bound kernels; the small-matrix (KEEP) kernels also exist as 128-thread CTAs
+// compiled for 7 CTAs per SM (<= 72 registers, 4144 warp slots) so that every warp of an L2-resident matrix is resident at once: a 121 k-row
+// matrix is 3788 warps, the 256-thread / 84-register form holds 3552 and leaves a 60 %-empty second wave.
+template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false, int NT = CTA>
+__global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
     if constexpr (KEEP) pdl_launch_dependents();
@@ -814,7 +819,7 @@ __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __
     const int local = bid - first;
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
     if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
-    run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * WARPS + warp, dyn_smem);
+    run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * (NT / 32) + warp, dyn_smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -822,11 +827,17 @@ __global__ void __launch_bounds__(CTA, KEEP ? 1 : MED_MINB) spmv_kernel(const __
 // above costs its own 128-byte L1 wavefront and its own 32-byte DRAM sector.  Here the live entries of ALL long rows
 // are sorted by (column block, row) at preprocessing (derive.cu); a CTA owns up to LCB_PART consecutive entries of one
 // block, stages that block of x (64 KB) in shared memory with TMA bulk copies (cp.async.bulk + mbarrier) while its
-// first value / index loads are in flight, and gathers from shared memory.  Every warp walks a contiguous slice; while
-// the row stays the same the lanes accumulate privately, a row change costs one warp reduction and one atomic add into
-// the per-row accumulator (the atomic merge of split rows, cf. longPart_sum src/dasp_f64.h:53-75).  The last CTA to
-// finish turns the accumulators into y (K11 placement, scatter / axpby forms included) and re-zeroes them.
+// first value / index loads are in flight, and gathers from shared memory.  A lane owns FOUR consecutive entries per step
+// (one 256-bit value load + one 128-bit load of packed row<<16|column indices): the load/store unit, not DRAM, bounds this
+// kernel, so instructions per entry are what counts.  Rows ascend inside a block: a lane first folds its own entries
+// (row changes inside a lane go straight to an atomic add), then while the whole warp stays on one row the lanes
+// accumulate privately; a row change costs ONE warp reduction + one atomic add into the per-row accumulator (the atomic
+// merge of split rows, cf. longPart_sum src/dasp_f64.h:53-75).  The last CTA to finish turns the accumulators into y (K11
+// placement, scatter / axpby forms included) and re-zeroes them.
 template <typename A> __device__ __forceinline__ void red_add(A *p, A v) { atomicAdd(p, v); }
+
+__device__ __forceinline__ void ld_lcb4(const double *p, double (&v)[4], const StreamPol &) { ld_stream4d<false>(p, v); }
+__device__ __forceinline__ void ld_lcb4(const __half *p, __half (&v)[4], const StreamPol &pol) { ld_stream4<false>(p, v, pol); }
 
 template <typename T>
 __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ SpmvArgs a)
@@ -862,66 +873,83 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     }
     for (int i = (int)(bytes16 / sizeof(T)) + tid; i < cnt; i += CTA) xs[i] = xg[i]; // tail that is not a 16-byte multiple
 
-    const int p0 = __ldg(a.lcb_blk_ptr + b), p1 = __ldg(a.lcb_blk_ptr + b + 1);
+    const int p0 = __ldg(a.lcb_blk_ptr + b), p1 = __ldg(a.lcb_blk_ptr + b + 1); // multiples of 4
     const int beg = p0 + (c - __ldg(a.lcb_cta_first + b)) * LCB_PART, end = min(beg + LCB_PART, p1);
-    const int per = ((end - beg + WARPS * 32 - 1) / (WARPS * 32)) * 32;
+    const int per = ((end - beg + WARPS * 128 - 1) / (WARPS * 128)) * 128;
     const int wbeg = beg + warp * per, wend = min(wbeg + per, end);
     const T *val = static_cast<const T *>(a.lcb_val);
     const StreamPol pol = make_stream_policy<false>();
-    constexpr int U = 4;
-    T v0[U], v1[U];
-    int c0[U], c1[U], r0[U], r1[U];
-    auto load = [&](T(&v)[U], int(&cc)[U], int(&rr)[U], int i) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int q = i + 32 * u + lane;
-            const bool ok = q < wend;
-            v[u] = ok ? ld_stream1(val + q, pol) : T(0);
-            cc[u] = ok ? ld_stream1(a.lcb_col + q, pol) : 0;
-            rr[u] = ok ? ld_stream1(a.lcb_row + q, pol) : -1;
-        }
-    };
     A *acc = static_cast<A *>(a.lcb_acc);
-    A lane_acc = 0;
-    int cur = -1;
-    auto flush = [&]() {
-        if (cur >= 0) {
-            const A t = warp_sum(lane_acc);
-            if (lane == 0) red_add(acc + cur, t);
-        }
-        lane_acc = 0;
-        cur = -1;
-    };
-    auto consume = [&](const T(&v)[U], const int(&cc)[U], const int(&rr)[U]) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            A p = to_acc(v[u]) * to_acc(xs[cc[u]]);
-            const int r = rr[u];
-            if (__all_sync(0xffffffffu, r == cur)) { lane_acc += p; continue; }
-            flush();
-            const int rf = __shfl_sync(0xffffffffu, r, 0);
-            if (rf >= 0 && __all_sync(0xffffffffu, r == rf)) { cur = rf; lane_acc = p; continue; }
-            // several rows in this group (rows ascend inside a block): segmented reduction towards the head lane of every run
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const A q = __shfl_down_sync(0xffffffffu, p, o);
-                const int rq = __shfl_down_sync(0xffffffffu, r, o);
-                if (lane + o < 32 && rq == r) p += q;
+    if (wbeg < wend) {
+        T v0[4], v1[4];
+        int k0[4], k1[4];
+        bool ok0, ok1;
+        // a lane past the end of the slice re-reads the indices of the slice's last four entries (rows stay ascending)
+        // and takes zeros as values
+        auto load = [&](T(&v)[4], int(&k)[4], bool &ok, int i) {
+            const int q = i + 4 * lane;
+            ok = q < wend;
+            const int qi = ok ? q : wend - 4;
+            if (i < wend) {
+                ld_stream4<false>(reinterpret_cast<const int *>(a.lcb_idx) + qi, k, pol);
+                if (ok) ld_lcb4(val + q, v, pol);
             }
-            const int rp = __shfl_up_sync(0xffffffffu, r, 1);
-            if ((lane == 0 || rp != r) && r >= 0) red_add(acc + r, p);
+        };
+        A lane_acc = 0;
+        int cur = -1; // row the private accumulators belong to
+        auto consume = [&](const T(&v)[4], const int(&k)[4], bool ok) {
+            A p[4];
+            int r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                r[j] = (int)((unsigned)k[ok ? j : 3] >> 16); // past the end: the row of the slice's last entry
+                p[j] = ok ? to_acc(v[j]) * to_acc(xs[k[j] & 0xFFFF]) : A(0);
+            }
+            if (__all_sync(0xffffffffu, r[0] == cur && r[3] == cur)) { lane_acc += (p[0] + p[1]) + (p[2] + p[3]); return; }
+            // Some row other than `cur` appears in this step.  Fold the lane's own entries: `first` = its leading run,
+            // `last` = its trailing run; runs in between (rows of fewer than 4 entries) go straight to the accumulators.
+            A first = p[0], last = p[0];
+            int last_row = r[0];
+            bool split = false; // the lane holds more than one row
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                if (r[j] == last_row) { last += p[j]; if (!split) first = last; }
+                else {
+                    if (split) red_add(acc + last_row, last); // a middle run
+                    split = true;
+                    last_row = r[j];
+                    last = p[j];
+                }
+            }
+            // everything that belongs to `cur`: the private accumulators and the leading runs that continue it
+            const A t = lane_acc + (r[0] == cur ? first : A(0));
+            const A total = warp_sum(t);
+            if (cur >= 0 && lane == 0) red_add(acc + cur, total);
+            const int new_cur = __shfl_sync(0xffffffffu, last_row, 31);
+            // leading run of a row other than cur / new_cur, or of new_cur when the lane continues with another row
+            if (r[0] != cur && (split || r[0] != new_cur)) red_add(acc + r[0], first);
+            if (split && last_row != new_cur) red_add(acc + last_row, last);
+            lane_acc = (last_row == new_cur) ? ((split || r[0] != cur) ? last : A(0)) : A(0);
+            cur = new_cur;
+        };
+        load(v0, k0, ok0, wbeg);
+        mbar_wait(bar_addr, 0);
+        __syncthreads(); // the tail elements written with plain stores
+        for (int i = wbeg; i < wend; i += 256) {
+            load(v1, k1, ok1, i + 128);
+            consume(v0, k0, ok0);
+            if (i + 128 >= wend) break;
+            load(v0, k0, ok0, i + 256);
+            consume(v1, k1, ok1);
         }
-    };
-    load(v0, c0, r0, wbeg);
-    mbar_wait(bar_addr, 0);
-    __syncthreads(); // the tail elements written with plain stores
-    for (int i = wbeg; i < wend; i += 64 * U) {
-        load(v1, c1, r1, i + 32 * U);
-        consume(v0, c0, r0);
-        load(v0, c0, r0, i + 64 * U);
-        consume(v1, c1, r1);
+        if (cur >= 0) {
+            const A total = warp_sum(lane_acc);
+            if (lane == 0) red_add(acc + cur, total);
+        }
+    } else {
+        mbar_wait(bar_addr, 0);
+        __syncthreads();
     }
-    flush();
     // completion: the last CTA of the launch writes y for every long row and re-arms the scratch
     __threadfence();
     __syncthreads();
@@ -1127,6 +1155,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
     a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
     a.reg_cbase = L.reg_cbase; a.reg_cdelta = L.reg_cdelta; a.blk_wide = h->index_compression ? L.blk_wide : nullptr;
+    a.blk_live = L.blk_live;
     a.row_long = s.row_long; a.row_block = s.row_block; a.blocknum = s.blocknum;
     a.short_val = L.short_val; a.short_cid = L.short_cid;
     a.n1 = s.short_row_1; a.c13 = s.common_13; a.n34 = s.short_row_34; a.n2 = s.short_row_2;
@@ -1151,7 +1180,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // away from the x gathers of the other categories); needs x on a 16-byte boundary for the TMA copies
     const bool use_lcb = lcb_selected(h) && ((uintptr_t)d_x & 15) == 0;
     if (use_lcb) {
-        a.lcb_val = L.lcb_val; a.lcb_col = L.lcb_col; a.lcb_row = L.lcb_row; a.lcb_blk_ptr = L.lcb_blk_ptr;
+        a.lcb_val = L.lcb_val; a.lcb_idx = L.lcb_idx; a.lcb_blk_ptr = L.lcb_blk_ptr;
         a.lcb_cta_first = L.lcb_cta_first; a.lcb_acc = L.lcb_acc; a.lcb_done = L.lcb_done;
         a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = s.n;
         if (!h->lcb_attr_set) {
@@ -1181,18 +1210,21 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.items[4] = on_short * (long)cdiv(tiles34, SHORT_TILES_PER_WARP);
     a.items[5] = on_short * (long)cdiv(tiles22, SHORT_TILES_PER_WARP);
     a.items[6] = on_zero * (long)cdiv(s.row_zero, 32);
+    // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
+    const bool keep = small && med != 1 && !mma_long && !tma_long && !mma_short;
+    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 128; // A/B aid: 256 = round-1 shape
+    const bool narrow = keep && keep_shape == 128;
+    const int nw = narrow ? 4 : WARPS;
     long total_items = 0;
     int acc_ctas = 0;
     for (int k = 0; k < 7; k++) {
-        acc_ctas += cdiv(a.items[k], WARPS);
+        acc_ctas += cdiv(a.items[k], nw);
         a.e[k] = acc_ctas;
         total_items += a.items[k];
     }
     if (total_items == 0) return DASP_OK;
     const int grid = a.e[6];
 
-    // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
-    const bool keep = small && med != 1 && !mma_long && !tma_long && !mma_short;
     // the kernels that use no shared memory ask for the whole unified array as L1 (x gathers live there), as the
     // reference does (src/dasp_f64.h:1280-1283)
 #define DASP_LAUNCH(T, MED, LV, KEEP)                                                                              \
@@ -1204,12 +1236,19 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         }                                                                                                          \
         if (KEEP) { /* small matrices: programmatic dependent launch hides the launch gap between products */     \
             cudaLaunchConfig_t cfg = {};                                                                            \
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;          \
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(narrow ? 128 : CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st; \
             cudaLaunchAttribute at[1];                                                                              \
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
             at[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
             cfg.attrs = at; cfg.numAttrs = 1;                                                                       \
-            DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<T, MED, LV, KEEP>, a));                                  \
+            if (narrow) {                                                                                           \
+                if (h->carved_narrow != (const void *)spmv_kernel<T, MED, LV, KEEP, false, 128>) {                  \
+                    cudaFuncSetAttribute(spmv_kernel<T, MED, LV, KEEP, false, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); \
+                    h->carved_narrow = (const void *)spmv_kernel<T, MED, LV, KEEP, false, 128>;                     \
+                }                                                                                                   \
+                DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<T, MED, LV, KEEP, false, 128>, a));                  \
+            } else                                                                                                  \
+                DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<T, MED, LV, KEEP>, a));                              \
         } else                                                                                                     \
             spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                     \
     } while (0)

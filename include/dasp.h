@@ -85,6 +85,10 @@ typedef struct dasp_stats_t {
     int64_t device_bytes;    /* device memory held by the handle                               */
     int col_min, col_max;    /* smallest / largest column index present (col_max = -1: no entries): the
                                 only part of x a product reads; dasp_spmv_host uploads just that range */
+    double long_gather_lines; /* diagnostic: estimated distinct 128-byte lines of x per 32-slot group of the long
+                                part (1 = dense ascending columns, 32 = every gather its own line); above the
+                                crossover AUTO uses the column-blocked long-row kernel (long_blocked != 0) */
+    int long_blocked, reserved_;
 } dasp_stats_t;
 
 /* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,

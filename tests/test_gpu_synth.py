@@ -124,7 +124,8 @@ def test_spec_literal_generators(cuda_device, kind):
             assert np.all(np.abs(cc - r * n / m) <= 2 * 512)
     else:
         assert lens.max() > 1000 and np.median(lens) <= 2
-        r = int(np.flatnonzero((lens >= 50) & (lens < 400))[0])
+        mid = (np.arange(m) > 5000) & (np.arange(m) < m - 5000)  # away from the border, where the window is clipped
+        r = int(np.flatnonzero((lens >= 50) & (lens < 400) & mid)[0])
         cc = ci[rp[r]:rp[r + 1]]
         inside = np.abs(cc - r * n / m) <= 512 + 1
         assert 0.85 <= inside.mean() <= 0.95
