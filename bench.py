@@ -51,11 +51,14 @@ def parse():
     ap.add_argument("--no-index-compression", action="store_true", help="A/B aid: kernels read reg_cid instead of the compact 16-bit indices")
     ap.add_argument("--categories", type=int, default=15, help="profiling aid: category mask (1 long, 2 medium, 4 short, 8 empty)")
     ap.add_argument("--breakdown", action="store_true", help="also time each row category alone (profiling aid)")
-    ap.add_argument("--exchange", default="bcast", choices=["bcast", "a2a", "p2p", "mc", "mcu", "p2pu", "mcc", "p2pc"],
-                    help="power iteration: how the y slabs reach every rank (bcast: one NCCL broadcast per slab; a2a: all-to-all "
+    ap.add_argument("--exchange", default="perm", choices=["perm", "bcast", "a2a", "p2p", "mc", "mcu", "p2pu", "mcc", "p2pc"],
+                    help="power iteration: how the y slabs reach every rank (perm, default: relabelled P*A*P^T mode, the iterate lives "
+                         "in permuted order, the SpMV kernel itself stores its slab of y, contiguous, into every rank's next x through one "
+                         "NVSwitch multicast mapping (peer mappings if there is none); the all-reduce of the norm is the only collective; bcast: one NCCL broadcast per slab; a2a: all-to-all "
                          "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs; p2p / mc: fused, the "
                          "SpMV kernel stores y straight into every peer's next x through NVLink peer mappings / one NVSwitch "
                          "multicast mapping, the all-reduce of the norm is the only collective)")
+    ap.add_argument("--no-iterated", action="store_true", help="skip the C5 100-step power-iteration leg (`iterated` key)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
     return ap.parse_args()
@@ -381,7 +384,9 @@ def run_ours(args):
         return ms
 
     if args.power_iter > 0:
-        power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz, timed)
+        res = power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz, timed)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
         h.close()
         if world > 1:
             dist.destroy_process_group()
@@ -433,6 +438,15 @@ def run_ours(args):
     e2e_ms = float(t[0].item()) / e2e_steps
     e2e_serial_ms = float(t[1].item()) / e2e_steps
 
+    # BASELINE config 5 (every N, so the scaling record carries it): 100-step power iteration on the skewed matrix as
+    # SURVEY 8(d) words it, row slabs over the N GPUs, the iterate exchanged every step
+    iterated = None
+    if args.workload == "c4" and not args.no_iterated and not args.no_others and not half:
+        try:
+            iterated = iterated_leg(args, dev, rank, world, local)
+        except Exception as e:  # never take the headline number down
+            iterated = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -471,6 +485,8 @@ def run_ours(args):
     }
     if breakdown:
         line["breakdown"] = breakdown
+    if iterated is not None:
+        line["iterated"] = iterated
 
     if world == 1 and not args.no_cpu and not half:
         try:
@@ -521,7 +537,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz_rank, timed):
+def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz_rank, timed, steps=None, exchange=None):
     """x <- A x / ||A x||_2, K steps.  Every rank multiplies its row slab (y written straight into its slab of
     the next x, original row order), the squared norm is all-reduced, the slab is scaled on the device and the
     slabs are exchanged with NCCL broadcasts (slab sizes differ under the nnz-balanced partition)."""
@@ -532,6 +548,8 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
 
     m, n = int(spec.m), int(spec.n)
     assert m == n, "power iteration needs a square matrix"
+    steps = steps or args.power_iter
+    exchange = exchange or args.exchange
     r0, r1 = cuts[rank], cuts[rank + 1]
     stream = torch.cuda.current_stream(dev).cuda_stream
     # The nnz-balanced slabs have very different row counts (C5: the rank holding the short rows owns almost all of
@@ -552,7 +570,25 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     recv_split = [overlap(cuts[p], cuts[p + 1], rank * chunk, min(m, (rank + 1) * chunk)) for p in range(world)]
     my_len = sum(recv_split)
 
-    fused = args.exchange in ("p2p", "mc", "mcu", "p2pu", "mcc", "p2pc") and world > 1
+    perm = exchange == "perm"
+    if perm:
+        # Relabelled mode: the global permuted index of original row j is (slab offset of its owner) + (that slab's inverse
+        # permutation of j); every rank relabels its columns with that map, so the iterate lives in permuted order and the
+        # slab product, left as the kernel produces it, IS this rank's contiguous slab of the next iterate.
+        order = torch.from_numpy(h.export("order_rid")).to(dev).long()
+        gmap = torch.empty(mp, dtype=torch.int32, device=dev)
+        gmap[r0 + order] = torch.arange(r0, r1, device=dev, dtype=torch.int32)
+        if world > 1:
+            for p in range(world):
+                if cuts[p + 1] > cuts[p]:
+                    dist.broadcast(gmap[cuts[p]:cuts[p + 1]], src=p)
+        h.relabel_columns(gmap, m)
+        xperm = torch.zeros(mp, dtype=torch.float64, device=dev)
+        xperm[gmap[:m].long()] = x
+        x = xperm[:m]
+        xa[:m].copy_(x)
+        del order
+    fused = (exchange in ("p2p", "mc", "mcu", "p2pu", "mcc", "p2pc") or perm) and world > 1
     if fused:
         # Fused product + exchange: both iterates live in symmetric memory; every rank's kernel stores its slab of y
         # into ALL copies of the next iterate (peer mappings or one multicast mapping).  The vector is kept
@@ -567,9 +603,9 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
         xa[:m].copy_(x)
         hdl.barrier()
         peer = [int(p) for p in hdl.buffer_ptrs]
-        use_mc = args.exchange in ("mc", "mcu", "mcc")
-        two_pass = args.exchange in ("mcu", "p2pu", "mcc", "p2pc")
-        copy_pass = args.exchange in ("mcc", "p2pc")
+        use_mc = exchange in ("mc", "mcu", "mcc") or (perm and int(hdl.multicast_ptr) != 0)
+        two_pass = exchange in ("mcu", "p2pu", "mcc", "p2pc")
+        copy_pass = exchange in ("mcc", "p2pc")
         yp = torch.zeros(max(r1 - r0, 1), dtype=torch.float64, device=dev) if two_pass else None
         token = torch.zeros(1, dtype=torch.float32, device=dev)
         mc_ptr = int(hdl.multicast_ptr) if use_mc else 0
@@ -603,9 +639,23 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
                 dist.all_reduce(token)  # orders every rank's stores into this rank's copy before the next product reads it
                 return
             # y_k = A x_k / ||y_{k-1}||  (x_k is stored un-normalised); the first step scales by 1
-            h.spmv_scatter_to(src, dests_of(dst), r0, nrm[k & 1], stream)
+            if perm:
+                h.spmv_permuted_to(src, dests_of(dst), r0, nrm[k & 1], stream)
+            else:
+                h.spmv_scatter_to(src, dests_of(dst), r0, nrm[k & 1], stream)
             dasp_b200.sumsq(dst.data_ptr() + r0 * esz, r1 - r0, nrm[(k + 1) & 1], stream)
             dist.all_reduce(nrm[(k + 1) & 1])
+            norm2.copy_(nrm[(k + 1) & 1])
+            fstate["k"] = k + 1
+    elif perm:  # one GPU, relabelled mode: the permuted product is the next iterate, scaled by the previous norm on the fly
+        nrm = [torch.ones(1, dtype=torch.float64, device=dev), torch.ones(1, dtype=torch.float64, device=dev)]
+        fstate = {"k": 0}
+        fused = True
+
+        def step(src, dst):
+            k = fstate["k"]
+            h.spmv_permuted_to(src, [dst], 0, nrm[k & 1], stream)
+            dasp_b200.sumsq(dst, m, nrm[(k + 1) & 1], stream)
             norm2.copy_(nrm[(k + 1) & 1])
             fstate["k"] = k + 1
     else:
@@ -617,7 +667,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
             dasp_b200.scale_rsqrt(dst.data_ptr() + r0 * esz, r1 - r0, norm2, stream)
             if world == 1:
                 return
-            if args.exchange == "bcast":
+            if exchange == "bcast":
                 works = [dist.broadcast(dst[cuts[p]:cuts[p + 1]], src=p, async_op=True)
                          for p in range(world) if cuts[p + 1] > cuts[p]]
                 for w in works:
@@ -642,7 +692,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.power_iter):
+    for _ in range(steps):
         step(xa, xb)
         xa, xb = xb, xa
     e1.record()
@@ -650,7 +700,7 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     lam = float(torch.sqrt(norm2).item())
     chk = float(xa[:m].sum().item())
-    if fused and args.exchange in ("p2p", "mc"):  # the iterate is stored un-normalised there
+    if fused and exchange in ("p2p", "mc", "perm"):  # the iterate is stored un-normalised there
         chk /= lam
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -659,28 +709,88 @@ def power_iteration(args, h, x, cuts, rank, world, dev, spec, wname, nnz_total, 
     if world > 1:
         dist.all_reduce(spmv_ms, op=dist.ReduceOp.MAX)
     if rank != 0:
-        return
-    step_ms = float(ms.item()) / args.power_iter
-    print(json.dumps({
+        return None
+    step_ms = float(ms.item()) / steps
+    return ({
         "metric": "power_iteration_gflops", "value": 2.0 * nnz_total / (step_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
-        "n_gpus": world, "steps": args.power_iter, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
+        "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname + f", {args.power_iter}-step power iteration", "m": m, "nnz": nnz_total,
+        "config": {"workload": wname + f", {steps}-step power iteration", "m": m, "nnz": nnz_total,
                    "partition": "nnz-balanced contiguous row slabs, x replicated",
                    "exchange": ("none (single GPU)" if world == 1 else
-                                "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if args.exchange == "bcast" else
-                                "fused: SpMV kernel stores y into every peer copy over NVLink P2P mappings; all_reduce(norm^2) only" if args.exchange == "p2p" else
-                                "fused: SpMV kernel stores y through one NVSwitch multicast mapping; all_reduce(norm^2) only" if args.exchange == "mc" else
-                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing through an NVSwitch multicast mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "mcu" else
-                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing to every peer mapping (dasp_unpermute_to) + token all_reduce" if args.exchange == "p2pu" else
-                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing through an NVSwitch multicast mapping (dasp_scale_copy_to) + token all_reduce" if args.exchange == "mcc" else
-                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing to every peer mapping (dasp_scale_copy_to) + token all_reduce" if args.exchange == "p2pc" else
+                                "relabelled P*A*P^T mode: the SpMV kernel stores its contiguous slab of the permuted product into every rank's next iterate through one NVSwitch multicast mapping (peer mappings without multicast); all_reduce(norm^2) is the only collective and the barrier" if exchange == "perm" else
+                                "all_reduce(norm^2) + one NCCL broadcast per non-empty slab per step" if exchange == "bcast" else
+                                "fused: SpMV kernel stores y into every peer copy over NVLink P2P mappings; all_reduce(norm^2) only" if exchange == "p2p" else
+                                "fused: SpMV kernel stores y through one NVSwitch multicast mapping; all_reduce(norm^2) only" if exchange == "mc" else
+                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing through an NVSwitch multicast mapping (dasp_unpermute_to) + token all_reduce" if exchange == "mcu" else
+                                "permuted SpMV + all_reduce(norm^2) + one coalesced un-permute/scale pass storing to every peer mapping (dasp_unpermute_to) + token all_reduce" if exchange == "p2pu" else
+                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing through an NVSwitch multicast mapping (dasp_scale_copy_to) + token all_reduce" if exchange == "mcc" else
+                                "SpMV into a local original-order slab + all_reduce(norm^2) + one coalesced scale/copy pass storing to every peer mapping (dasp_scale_copy_to) + token all_reduce" if exchange == "p2pc" else
                                 "all_reduce(norm^2) + NCCL all_to_all of slab pieces into P equal chunks + all_gather of the chunks"),
                    "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]},
         "spmv_only_ms": float(spmv_ms.item()), "exchange_and_vector_ms": step_ms - float(spmv_ms.item()),
         "eigenvalue_estimate": lam, "x_checksum": chk,
-        "gpu_launches": args.power_iter * (h.launches_per_spmv() + 3),
-    }), flush=True)
+        "gpu_launches": steps * (h.launches_per_spmv() + 3),
+    })
+
+
+def iterated_leg(args, dev, rank, world, local):
+    """C5 (skewed_spec, full size) as a 100-step power iteration x <- A x / ||A x|| on `world` GPUs: nnz-balanced contiguous
+    row slabs (the long rows sit at seeded positions, so the slabs are balanced in rows as well), iterate replicated,
+    exchanged every step.  Returns a compact dict: per-step time of the fused relabelled exchange and (N > 1) of the plain
+    NCCL broadcast exchange, SpMV-only time, eigenvalue estimate and checksum (identical for every N and exchange)."""
+    import copy
+
+    import torch
+
+    import dasp_b200
+    from dasp_b200 import synth
+
+    a = copy.copy(args)
+    a.workload, a.scale, a.power_iter = "c5_spec", 1.0, 100
+    spec, wname, _ = make_spec(a)
+    m = int(spec.m)
+    ln = synth.row_lengths(spec, 0, m, dev)
+    cs = torch.cumsum(ln, 0)
+    nnz_total = int(cs[-1].item())
+    targets = torch.tensor([nnz_total * p // world for p in range(1, world)], device=dev, dtype=torch.int64)
+    cuts = [0] + [min(int(c) + 1, m) for c in torch.searchsorted(cs, targets, right=False).tolist()] + [m]
+    del ln, cs
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    rp, ci, v, nnz = synth.generate(spec, r0, r1, dev)
+    out = {"workload": wname + ", 100-step power iteration", "m": m, "nnz": nnz_total, "n_gpus": world,
+           "slab_rows": [cuts[p + 1] - cuts[p] for p in range(world)]}
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    x = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * 2 - 1
+    y = torch.zeros(max(r1 - r0, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for exchange in (("perm", "bcast") if world > 1 else ("perm",)):
+        h = dasp_b200.Dasp(dasp_b200.DASP_F64, r1 - r0, m, rp, ci, v, device=local, nnz=nnz)
+
+        def timed(k, w, h=h):
+            for _ in range(w):
+                h.spmv(x, y, stream)
+            torch.cuda.synchronize(dev)
+            return h.spmv_timed(x, y, stream, 0, k)
+
+        res = power_iteration(a, h, x, cuts, rank, world, dev, spec, wname, nnz_total, nnz, timed, steps=100, exchange=exchange)
+        h.close()
+        if res is not None:
+            key = "fused_relabelled" if exchange == "perm" else "nccl_broadcast"
+            out[key] = {"ms_per_step": res["ms_per_step"], "gflops": res["value"], "spmv_only_ms": res["spmv_only_ms"],
+                        "exchange_and_vector_ms": res["exchange_and_vector_ms"], "eigenvalue_estimate": res["eigenvalue_estimate"],
+                        "x_checksum": res["x_checksum"], "exchange": res["config"]["exchange"]}
+    del rp, ci, v, x, y
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    best = out["fused_relabelled"]
+    out.update({"steps": 100, "ms_per_step": best["ms_per_step"], "gflops": best["gflops"],
+                "limiter": ("one GPU: the product itself" if world == 1 else
+                            "per step every GPU multicasts its %.0f MB slab and receives %.0f MB over NVLink; the stores are issued by the SpMV kernel as rows finish, the 8-byte all-reduce of the norm is the only collective"
+                            % ((cuts[1] - cuts[0]) * 8 / 1e6, (m - (cuts[1] - cuts[0])) * 8 / 1e6))})
+    return out
 
 
 def other_configs(args, dev):

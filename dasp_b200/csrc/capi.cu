@@ -199,6 +199,41 @@ int dasp_spmv_scatter_to(dasp_handle *h, const void *d_x, void *const *d_dests, 
     return launch_spmv(h, d_x, d_dests[0], h->L.order_rid, (cudaStream_t)stream, nullptr, &m);
 }
 
+int dasp_spmv_permuted_to(dasp_handle *h, const void *d_x, void *const *d_dests, int n_dests, int64_t row_offset,
+                          const double *d_norm2, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || !d_dests || n_dests < 1 || n_dests > 8 || row_offset < 0) {
+        set_error("dasp_spmv_permuted_to: bad argument (1..8 destinations)");
+        return DASP_ERR_INVALID;
+    }
+    ScatterTo m{};
+    for (int p = 0; p < n_dests; p++) {
+        if (!d_dests[p]) { set_error("dasp_spmv_permuted_to: destination %d is NULL", p); return DASP_ERR_INVALID; }
+        if (p > 0) m.extra[p - 1] = d_dests[p];
+    }
+    m.n_extra = n_dests - 1;
+    m.row_offset = row_offset;
+    m.norm2 = d_norm2;
+    DASP_ON_DEVICE(h->device);
+    return launch_spmv(h, d_x, d_dests[0], nullptr, (cudaStream_t)stream, nullptr, &m);
+}
+
+int dasp_relabel_columns(dasp_handle *h, const int *d_new_index, int n_new)
+{
+    if (!h || (!d_new_index && h->L.s.n > 0) || n_new < 0) { set_error("dasp_relabel_columns: bad argument"); return DASP_ERR_INVALID; }
+    if (!is_device_ptr(d_new_index) && h->L.s.n > 0) { set_error("dasp_relabel_columns: new_index must be a device pointer"); return DASP_ERR_INVALID; }
+    DASP_ON_DEVICE(h->device);
+    DASP_CUDA(cudaDeviceSynchronize()); // new_index may have been produced on another stream; no product may be in flight
+    return relabel_columns(h, d_new_index, n_new, h->own_stream);
+}
+
+int dasp_inverse_order(const dasp_handle *h, const int **d_inv_order)
+{
+    if (!h || !d_inv_order) { set_error("dasp_inverse_order: NULL argument"); return DASP_ERR_INVALID; }
+    *d_inv_order = h->L.inv_order;
+    return DASP_OK;
+}
+
 int dasp_unpermute_to(dasp_handle *h, const void *d_y_perm, void *const *d_dests, int n_dests, int64_t row_offset,
                       const double *d_norm2, void *stream)
 {

@@ -86,6 +86,11 @@ struct Layout {
     int *reg_cid = nullptr;
     void *short_val = nullptr;
     int *short_cid = nullptr;
+    // ---- column indices the kernels actually read: the reference arrays above, or — after dasp_relabel_columns — relabelled
+    // copies (the reference arrays stay bit-exact and exportable) ----
+    int *k_long_cid = nullptr, *k_reg_cid = nullptr, *k_irreg_cid = nullptr, *k_short_cid = nullptr;
+    int relabelled = 0;
+    int x_len = 0; // length of the x the kernels index (n, or the size of the relabelled index space)
     // ---- derived launch data of this implementation (not part of the reference layout) ----
     int n_long_units = 0;
     int *long_unit_row = nullptr;   // [n_long_units] long row of each unit (execution order)
@@ -159,6 +164,8 @@ int radix_sort_pairs(DevicePool &tmp, const int *keys_in, const int *vals_in, in
 // derive.cu: kernel-facing data derived from the reference layout (also after dasp_load); build_lcb on demand
 int derive(dasp_handle *h, cudaStream_t st);
 int build_lcb(dasp_handle *h, cudaStream_t st);
+// kernel-facing column indices := new_index[reference column]; compact indices and the column-blocked copy are rebuilt
+int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStream_t st);
 // range / monotonicity check of the offset and index arrays of a layout read from a file (dasp_load)
 int validate_layout(dasp_handle *h, cudaStream_t st);
 int preprocess(dasp_handle *h, int m, int n, int64_t nnz, const int *d_rowptr, const int *d_colidx,

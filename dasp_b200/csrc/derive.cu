@@ -141,14 +141,13 @@ __global__ void lcb_warp_rows(const int *__restrict__ long_rpt_new, int row_long
 
 // sort key of every slot of the padded long part: its column block; padding (value 0 AND column 0) sorts last
 template <typename T>
-__global__ void lcb_keys(const T *__restrict__ long_val, const int *__restrict__ long_cid, int slots, int bw_log2, int nblk,
-                         int *__restrict__ key, int *__restrict__ idx)
+__global__ void lcb_keys(const T *__restrict__ long_val, const int *__restrict__ ref_cid, const int *__restrict__ long_cid, int slots,
+                         int bw_log2, int nblk, int *__restrict__ key, int *__restrict__ idx)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= slots) return;
-    const int c = long_cid[p];
-    const bool live = !(c == 0 && long_val[p] == T(0));
-    key[p] = live ? (c >> bw_log2) : nblk;
+    const bool live = !(ref_cid[p] == 0 && long_val[p] == T(0)); // padding as the reference writes it
+    key[p] = live ? (long_cid[p] >> bw_log2) : nblk;
     idx[p] = p;
 }
 
@@ -207,7 +206,7 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     const int slots = s.fill0_nnz_long, longw = sizeof(T) == 2 ? 256 : 64;
     int bw_log2 = 0;
     while ((sizeof(T) << (bw_log2 + 1)) <= (size_t)LCB_BYTES) bw_log2++; // 8192 doubles / 32768 halves
-    const int nblk = s.n > 0 ? (int)((((int64_t)s.n - 1) >> bw_log2) + 1) : 1;
+    const int nblk = L.x_len > 0 ? (int)((((int64_t)L.x_len - 1) >> bw_log2) + 1) : 1;
     int *warp_row = nullptr, *key = nullptr, *idx = nullptr, *skey = nullptr, *sidx = nullptr, *blk_ptr = nullptr;
     DASP_TRY(tmp.alloc((void **)&warp_row, sizeof(int) * (size_t)s.warp_number));
     DASP_TRY(tmp.alloc((void **)&key, sizeof(int) * (size_t)slots));
@@ -217,7 +216,7 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     DASP_TRY(tmp.alloc((void **)&blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
     DASP_CUDA(cudaMemsetAsync(warp_row, 0, sizeof(int) * (size_t)s.warp_number, st));
     lcb_warp_rows<<<s.row_long, 256, 0, st>>>(L.long_rpt_new, s.row_long, warp_row);
-    lcb_keys<T><<<grid_for(slots, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, slots, bw_log2, nblk, key, idx);
+    lcb_keys<T><<<grid_for(slots, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, L.k_long_cid, slots, bw_log2, nblk, key, idx);
     int bits = 1;
     while ((1 << bits) <= nblk) bits++;
     DASP_TRY(radix_sort_pairs(tmp, key, idx, skey, sidx, slots, bits, false, st));
@@ -240,7 +239,7 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     DASP_CUDA(cudaMemsetAsync(L.lcb_acc, 0, 8 * (size_t)s.row_long, st));
     DASP_CUDA(cudaMemsetAsync(L.lcb_done, 0, sizeof(unsigned) * 4, st));
     if (total > 0)
-        lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
+        lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.k_long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
                                                            nblk, total, longw, (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_idx);
     DASP_CUDA(cudaGetLastError());
     DASP_CUDA(cudaStreamSynchronize(st)); // the scratch is released by the guard
@@ -329,6 +328,132 @@ int build_lcb(dasp_handle *h, cudaStream_t st)
     return rc;
 }
 
+namespace {
+
+template <typename T>
+__global__ void map_cid(const int *__restrict__ src, const T *__restrict__ val, long count, const int *__restrict__ map,
+                        int *__restrict__ dst)
+{
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        const int c = src[i];
+        // padding slots (column 0, value 0) keep pointing at x[0]: they must stay recognisable and inside x
+        dst[i] = (c == 0 && val && val[i] == T(0)) ? 0 : map[c];
+    }
+}
+
+// compact forms of the kernel-facing column indices (and the estimate that decides chunked vs column-blocked long rows)
+int derive_indices(dasp_handle *h, cudaStream_t st, unsigned long long *lines)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    const int cl = s.row_long, blocknum = s.blocknum;
+    const int longw = h->dtype == DASP_F16 ? 256 : 64, esz = (int)L.esz;
+    if (cl > 0 && L.n_long_units > 0)
+        compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(
+            L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.k_long_cid, L.n_long_units, longw, LONG_UNIT_WARPS, esz,
+            L.long_cbase, L.long_cdelta, L.long_wide, lines);
+    if (blocknum > 0) {
+        if (h->dtype == DASP_F16)
+            compress_cid<unsigned short><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
+                L.blockPtr, L.k_reg_cid, (const unsigned short *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
+        else
+            compress_cid<double><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
+                L.blockPtr, L.k_reg_cid, (const double *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
+    }
+    DASP_CUDA(cudaGetLastError());
+    return DASP_OK;
+}
+
+// chunked or column-blocked long rows: average number of distinct 128-byte lines of x that one 32-lane gather of the
+// chunked kernel touches (estimated from the column span of every 32-slot group)
+int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long long *lines)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    L.long_lines_avg = 0.0;
+    h->lcb_auto = 0;
+    L.s.long_gather_lines = 0.0;
+    L.s.long_blocked = 0;
+    if (s.row_long > 0 && s.fill0_nnz_long > 0) {
+        unsigned long long nl = 0;
+        DASP_CUDA(cudaMemcpyAsync(&nl, lines, sizeof(nl), cudaMemcpyDeviceToHost, st));
+        DASP_CUDA(cudaStreamSynchronize(st));
+        L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
+        L.s.long_gather_lines = L.long_lines_avg;
+        double thr = 12.0; // measured crossover, profiles/r02/README.md
+        if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
+        if (L.long_lines_avg > thr && s.row_long <= 65535 && s.nnz_long >= 4 * LCB_PART) {
+            DASP_TRY(build_lcb(h, st));
+            h->lcb_auto = L.lcb_nctas > 0;
+            L.s.long_blocked = h->lcb_auto;
+        }
+    }
+    return DASP_OK;
+}
+
+} // namespace
+
+int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    DevicePool &pool = h->pool;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    if (s.n > 0) { // every new index must lie inside the relabelled x
+        int *flag = nullptr, bad = 0;
+        DASP_TRY(tmp.alloc((void **)&flag, sizeof(int)));
+        DASP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        check_range<<<592, 256, 0, st>>>(d_new_index, s.n, n_new, flag);
+        DASP_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DASP_CUDA(cudaStreamSynchronize(st));
+        if (bad) { set_error("dasp_relabel_columns: a new index lies outside [0, %d)", n_new); return DASP_ERR_INVALID; }
+    }
+    if (!L.relabelled) {
+        int *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+        DASP_TRY(pool.alloc((void **)&a, sizeof(int) * (size_t)s.fill0_nnz_long));
+        DASP_TRY(pool.alloc((void **)&b, sizeof(int) * (size_t)s.fill0_nnz_reg));
+        DASP_TRY(pool.alloc((void **)&c, sizeof(int) * (size_t)s.nnz_irreg));
+        DASP_TRY(pool.alloc((void **)&d, sizeof(int) * (size_t)s.fill0_nnz_short));
+        L.k_long_cid = a; L.k_reg_cid = b; L.k_irreg_cid = c; L.k_short_cid = d;
+        L.relabelled = 1;
+    }
+    const int G = 1184;
+    if (h->dtype == DASP_F16) {
+        using H = unsigned short;
+        map_cid<H><<<G, 256, 0, st>>>(L.long_cid, (const H *)L.long_val, s.fill0_nnz_long, d_new_index, L.k_long_cid);
+        map_cid<H><<<G, 256, 0, st>>>(L.reg_cid, (const H *)L.reg_val, s.fill0_nnz_reg, d_new_index, L.k_reg_cid);
+        map_cid<H><<<G, 256, 0, st>>>(L.irreg_cid, (const H *)nullptr, s.nnz_irreg, d_new_index, L.k_irreg_cid);
+        map_cid<H><<<G, 256, 0, st>>>(L.short_cid, (const H *)L.short_val, s.fill0_nnz_short, d_new_index, L.k_short_cid);
+    } else {
+        map_cid<double><<<G, 256, 0, st>>>(L.long_cid, (const double *)L.long_val, s.fill0_nnz_long, d_new_index, L.k_long_cid);
+        map_cid<double><<<G, 256, 0, st>>>(L.reg_cid, (const double *)L.reg_val, s.fill0_nnz_reg, d_new_index, L.k_reg_cid);
+        map_cid<double><<<G, 256, 0, st>>>(L.irreg_cid, (const double *)nullptr, s.nnz_irreg, d_new_index, L.k_irreg_cid);
+        map_cid<double><<<G, 256, 0, st>>>(L.short_cid, (const double *)L.short_val, s.fill0_nnz_short, d_new_index, L.k_short_cid);
+    }
+    DASP_CUDA(cudaGetLastError());
+    L.x_len = n_new;
+    L.s.col_min = 0; L.s.col_max = n_new - 1; // the host paths upload the whole relabelled vector
+    unsigned long long *lines = nullptr;
+    DASP_TRY(tmp.alloc((void **)&lines, sizeof(unsigned long long)));
+    DASP_CUDA(cudaMemsetAsync(lines, 0, sizeof(unsigned long long), st));
+    DASP_TRY(derive_indices(h, st, lines));
+    // the column-blocked copy depends on the labels: drop it and let the decision run again on the new ones
+    const bool had_lcb = L.lcb_val != nullptr;
+    if (had_lcb) {
+        DASP_CUDA(cudaStreamSynchronize(st));
+        pool.release(L.lcb_val); pool.release(L.lcb_idx); pool.release(L.lcb_blk_ptr); pool.release(L.lcb_cta_first);
+        pool.release(L.lcb_acc); pool.release(L.lcb_done);
+        L.lcb_val = nullptr; L.lcb_idx = nullptr; L.lcb_blk_ptr = nullptr; L.lcb_cta_first = nullptr; L.lcb_acc = nullptr;
+        L.lcb_done = nullptr; L.lcb_nctas = 0; L.lcb_live = 0;
+    }
+    DASP_TRY(decide_long_variant(h, st, lines));
+    if (h->var_long == DASP_VARIANT_BLOCKED && !L.lcb_val) DASP_TRY(build_lcb(h, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    h->L.s.device_bytes = h->pool.bytes;
+    return DASP_OK;
+}
+
 int derive(dasp_handle *h, cudaStream_t st)
 {
     Layout &L = h->L;
@@ -337,7 +462,9 @@ int derive(dasp_handle *h, cudaStream_t st)
     DevicePool tmp;
     struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
     const int cl = s.row_long, cm = s.row_block, blocknum = s.blocknum, m = s.m;
-    const int longw = h->dtype == DASP_F16 ? 256 : 64, esz = (int)L.esz;
+    L.k_long_cid = L.long_cid; L.k_reg_cid = L.reg_cid; L.k_irreg_cid = L.irreg_cid; L.k_short_cid = L.short_cid;
+    L.relabelled = 0;
+    L.x_len = s.n;
 
     // ---- long rows: work units (execution order), merge scratch, compact indices ----
     DASP_TRY(pool.alloc((void **)&L.long_unit_first, sizeof(int) * (size_t)(cl + 1)));
@@ -360,12 +487,8 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(pool.alloc((void **)&L.long_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_long));
     DASP_TRY(pool.alloc((void **)&L.long_wide, (size_t)L.n_long_units));
     DASP_CUDA(cudaMemsetAsync(L.long_done, 0, sizeof(unsigned) * (size_t)cl, st));
-    if (cl > 0 && L.n_long_units > 0) {
+    if (cl > 0 && L.n_long_units > 0)
         fill_long_units<<<(cl + 7) / 8, 128, 0, st>>>(L.long_unit_first, cl, L.long_unit_row, L.long_unit_chunk);
-        compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(
-            L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.long_cid, L.n_long_units, longw, LONG_UNIT_WARPS, esz,
-            L.long_cbase, L.long_cdelta, L.long_wide, lines);
-    }
     // ---- medium rows: irregular-tail flags, compact indices ----
     const int ngroups = ceil_div(cm, 32);
     DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
@@ -374,39 +497,14 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
     DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
     if (cm > 0) flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
-    if (blocknum > 0) {
-        if (h->dtype == DASP_F16)
-            compress_cid<unsigned short><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
-                L.blockPtr, L.reg_cid, (const unsigned short *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
-        else
-            compress_cid<double><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
-                L.blockPtr, L.reg_cid, (const double *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
-    }
+    DASP_TRY(derive_indices(h, st, lines));
     // ---- inverse permutation (dasp_unpermute_to, relabelled mode) ----
     DASP_TRY(pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
     if (m > 0) invert_order<<<grid_for(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
     DASP_CUDA(cudaGetLastError());
 
-    // ---- scattered long rows: column-blocked copy.  Decision: average number of distinct 128-byte lines of x that one
-    // 32-lane gather of the chunked kernel touches (estimated from the column span of every 32-slot group) ----
-    L.long_lines_avg = 0.0;
-    h->lcb_auto = 0;
-    L.s.long_gather_lines = 0.0;
-    L.s.long_blocked = 0;
-    if (cl > 0 && s.fill0_nnz_long > 0) {
-        unsigned long long nl = 0;
-        DASP_CUDA(cudaMemcpyAsync(&nl, lines, sizeof(nl), cudaMemcpyDeviceToHost, st));
-        DASP_CUDA(cudaStreamSynchronize(st));
-        L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
-        L.s.long_gather_lines = L.long_lines_avg;
-        double thr = 12.0; // measured crossover, profiles/r02/README.md
-        if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
-        if (L.long_lines_avg > thr && cl <= 65535 && s.nnz_long >= 4 * LCB_PART) {
-            DASP_TRY(build_lcb(h, st));
-            h->lcb_auto = L.lcb_nctas > 0;
-            L.s.long_blocked = h->lcb_auto;
-        }
-    }
+    // ---- scattered long rows: column-blocked copy ----
+    DASP_TRY(decide_long_variant(h, st, lines));
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

@@ -233,6 +233,22 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// FP16 tensor-core step: D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)  -> SASS HMMA.16816.F32.
+// The reference's FP16 kernels use mma.m8n8k4.f16 (src/dasp_f16.h:31-75), which sm_100a only emulates; m16n8k16 is the
+// native shape.  Fragment map: lane (g = lane>>2, t = lane&3) holds A[g][2t,2t+1] (a0), A[g+8][..] (a1), A[g][2t+8,2t+9]
+// (a2), A[g+8][..] (a3), B[2t,2t+1][g] (b0), B[2t+8,2t+9][g] (b1), D[g][2t,2t+1] (d0,d1), D[g+8][..] (d2,d3).
+// DASP use: A row g = 16 consecutive entries of matrix row g (four 8x4 tiles), B column g = x gathered for exactly those
+// entries by the SAME lane, so D[g][g] is the dot product; rows 8..15 of A are zero (a1 = a3 = 0).
+__device__ __forceinline__ void hmma16816(float (&d)[4], unsigned a0, unsigned a2, unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_half2(__half lo, __half hi)
+{
+    return (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+}
+
 // ------------------------------------------------------------------------------------------------
 // long rows
 
@@ -276,6 +292,26 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
         const int n0 = 2 * (lane & 3);
         double d = (n0 == grp ? c[0] : 0.0) + (n0 + 1 == grp ? c[1] : 0.0);
         acc = (A)warp_sum(d);
+    } else if constexpr (MMA && sizeof(T) == 2) {
+        // FP16 tensor-core variant: 128 slots per HMMA step, lane (g, t) owns slots p + 16 g + 4 t .. +3 (one 64-bit value
+        // load, one 128-bit index load, four gathers); the eight partial sums sit on the diagonal of D.
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const int g = lane >> 2, t = lane & 3;
+        const __half *hval = reinterpret_cast<const __half *>(val);
+        const __half *hx = reinterpret_cast<const __half *>(x);
+        for (long p = beg + 16 * g + 4 * t; p < end; p += 128) { // units are multiples of 256 slots: no partial step
+            __half v[4];
+            int c[4];
+            ld_stream4<KEEP>(hval + p, v, pol);
+            ld_stream4<KEEP>(a.long_cid + p, c, pol);
+            __half xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) xv[j] = __ldg(hx + c[j]);
+            hmma16816(d, pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(xv[0], xv[1]), pack_half2(xv[2], xv[3]));
+        }
+        const int n0 = 2 * t; // D[g][n0], D[g][n0+1]: keep only the diagonal
+        const float dd = (n0 == g ? d[0] : 0.f) + (n0 + 1 == g ? d[1] : 0.f);
+        acc = (A)warp_sum(dd);
     } else if constexpr (LONGV == 2) {
         // The dense value/index streams of the unit are moved by TMA 1-D bulk copies into a 3-stage shared-memory
         // ring owned by this warp (lane 0 is the producer, one mbarrier per stage); the lanes read their slots from
@@ -444,6 +480,46 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
             // C[r][r] sits in lane 4r + (r>>1), register r&1; route it to lane 8i + r
             const int r = lane & 7, src = 4 * r + (r >> 1);
             double v0 = __shfl_sync(0xffffffffu, c[0], src), v1 = __shfl_sync(0xffffffffu, c[1], src);
+            if ((lane >> 3) == i) acc = (A)((r & 1) ? v1 : v0);
+        }
+    } else if constexpr (MMA && sizeof(T) == 2) {
+        // FP16 tensor-core variant (HMMA.16816.F32): per step four 8x4 tiles of one block; lane (q, t) owns row q of tile
+        // k + t: one 64-bit value load + one 128-bit index load + four gathers feed A[q][..] and B[..][q] of the same lane.
+        // FP16 blocks are multiples of 4 tiles (src/dasp_f16.h:1356); all-zero trailing steps are skipped (blk_live).
+        const __half *hval = reinterpret_cast<const __half *>(val);
+        const __half *hx = reinterpret_cast<const __half *>(x);
+        const int q = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int b = group * 4 + i;
+            const int bp0 = __ldg(a.blockPtr + b), bp1 = __ldg(a.blockPtr + b + 1);
+            const int nt = min((bp1 - bp0) >> 5, ((int)__ldg(a.blk_live + b) + 3) & ~3);
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const __half *pv = hval + bp0 + 32 * t + 4 * q;
+            const int *pc = a.reg_cid + bp0 + 32 * t + 4 * q;
+            for (int k = 0; k < nt; k += 8) { // two steps in flight
+                __half v[2][4], xv[2][4];
+                int c[2][4];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (k + 4 * j < nt) { ld_stream4<KEEP>(pv + 32 * (k + 4 * j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + 4 * j), c[j], pol); }
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) { v[j][e] = __ushort_as_half(0); c[j][e] = 0; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) xv[j][e] = __ldg(hx + c[j][e]);
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                    hmma16816(d, pack_half2(v[j][0], v[j][1]), pack_half2(v[j][2], v[j][3]), pack_half2(xv[j][0], xv[j][1]),
+                              pack_half2(xv[j][2], xv[j][3]));
+            }
+            // D[r][r] sits in lane 4r + (r>>1), register r&1; route it to lane 8i + r
+            const int r = lane & 7, src = 4 * r + (r >> 1);
+            const float v0 = __shfl_sync(0xffffffffu, d[0], src), v1 = __shfl_sync(0xffffffffu, d[1], src);
             if ((lane >> 3) == i) acc = (A)((r & 1) ? v1 : v0);
         }
     } else {
@@ -1148,16 +1224,16 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         a.row_offset = (long)multi->row_offset;
         a.rs_ptr = multi->norm2;
     }
-    a.long_val = L.long_val; a.long_cid = L.long_cid; a.long_rpt_new = L.long_rpt_new;
+    a.long_val = L.long_val; a.long_cid = L.k_long_cid; a.long_rpt_new = L.long_rpt_new;
     a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
     a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
     a.long_cbase = L.long_cbase; a.long_cdelta = L.long_cdelta; a.long_wide = h->index_compression ? L.long_wide : nullptr;
-    a.reg_val = L.reg_val; a.reg_cid = L.reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
-    a.irreg_val = L.irreg_val; a.irreg_cid = L.irreg_cid; a.has_irreg = L.med_has_irreg;
+    a.reg_val = L.reg_val; a.reg_cid = L.k_reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
+    a.irreg_val = L.irreg_val; a.irreg_cid = L.k_irreg_cid; a.has_irreg = L.med_has_irreg;
     a.reg_cbase = L.reg_cbase; a.reg_cdelta = L.reg_cdelta; a.blk_wide = h->index_compression ? L.blk_wide : nullptr;
     a.blk_live = L.blk_live;
     a.row_long = s.row_long; a.row_block = s.row_block; a.blocknum = s.blocknum;
-    a.short_val = L.short_val; a.short_cid = L.short_cid;
+    a.short_val = L.short_val; a.short_cid = L.k_short_cid;
     a.n1 = s.short_row_1; a.c13 = s.common_13; a.n34 = s.short_row_34; a.n2 = s.short_row_2;
     const int f13 = s.fill0_nnz_short13, f34 = s.fill0_nnz_short34, f22 = s.fill0_nnz_short22;
     a.s1 = f16 ? f13 + f34 + f22 : 0;
@@ -1182,7 +1258,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     if (use_lcb) {
         a.lcb_val = L.lcb_val; a.lcb_idx = L.lcb_idx; a.lcb_blk_ptr = L.lcb_blk_ptr;
         a.lcb_cta_first = L.lcb_cta_first; a.lcb_acc = L.lcb_acc; a.lcb_done = L.lcb_done;
-        a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = s.n;
+        a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = L.x_len;
         if (!h->lcb_attr_set) {
             DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
             DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
@@ -1198,9 +1274,9 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // alternatives: both lose on B200 (profiles/r01/variants.md).
     const bool small = s.data_X <= ((int64_t)48 << 20); // B200 L2: 126 MB over two dies
     int med = 0;
-    if (h->var_medium == DASP_VARIANT_MMA && !f16) med = 1;
+    if (h->var_medium == DASP_VARIANT_MMA) med = 1; // FP64: DMMA m8n8k4; FP16: HMMA m16n8k16
     else if (h->var_medium == DASP_VARIANT_SPLIT) med = 2;
-    const bool mma_long = !f16 && h->var_long == DASP_VARIANT_MMA && !use_lcb;
+    const bool mma_long = h->var_long == DASP_VARIANT_MMA && !use_lcb;
     const bool tma_long = h->var_long == DASP_VARIANT_TMA && !use_lcb;
     const bool mma_short = !f16 && h->var_short == DASP_VARIANT_MMA;
     a.items[0] = on_long * (long)L.n_long_units;
@@ -1254,6 +1330,8 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     } while (0)
     if (f16) {
         if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
+        else if (mma_long) { if (med == 1) DASP_LAUNCH(__half, 1, 1, false); else DASP_LAUNCH(__half, 0, 1, false); }
+        else if (med == 1) DASP_LAUNCH(__half, 1, 0, false);
         else if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, 0, true); else DASP_LAUNCH(__half, 2, 0, false); }
         else { if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
     } else if (mma_short) { // DMMA short rows (comparison variant): with the plain or the DMMA long / medium paths

@@ -87,6 +87,9 @@ def load() -> C.CDLL:
         L.dasp_spmv_host.argtypes = [vp, vp, vp]
         L.dasp_spmv_scatter_to.argtypes = [vp, vp, C.POINTER(vp), ip, C.c_int64, vp, vp]
         L.dasp_unpermute_to.argtypes = [vp, vp, C.POINTER(vp), ip, C.c_int64, vp, vp]
+        L.dasp_spmv_permuted_to.argtypes = [vp, vp, C.POINTER(vp), ip, C.c_int64, vp, vp]
+        L.dasp_relabel_columns.argtypes = [vp, vp, ip]
+        L.dasp_inverse_order.argtypes = [vp, C.POINTER(vp)]
         L.dasp_spmv_host_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
         L.dasp_spmv_axpby.argtypes = [vp, C.c_double, vp, C.c_double, vp, ip, vp]
         L.dasp_save.argtypes = [vp, C.c_char_p]
@@ -194,6 +197,21 @@ class Dasp:
         arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
         _check(load().dasp_spmv_scatter_to(self._h, _ptr(d_x), arr, len(dests), row_offset, _ptr(d_norm2), C.c_void_p(stream)),
                "dasp_spmv_scatter_to")
+
+    def spmv_permuted_to(self, d_x, dests, row_offset: int, d_norm2=None, stream: int = 0) -> None:
+        """Slab product in PERMUTED order, scaled by 1/sqrt(*d_norm2), stored at row_offset of every vector in `dests`."""
+        arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
+        _check(load().dasp_spmv_permuted_to(self._h, _ptr(d_x), arr, len(dests), row_offset, _ptr(d_norm2), C.c_void_p(stream)),
+               "dasp_spmv_permuted_to")
+
+    def relabel_columns(self, d_new_index, n_new: int) -> None:
+        """Kernel-facing column indices := new_index[column] (device int32 array); x then lives in the new index space."""
+        _check(load().dasp_relabel_columns(self._h, _ptr(d_new_index), n_new), "dasp_relabel_columns")
+
+    def inverse_order_ptr(self) -> int:
+        p = C.c_void_p(None)
+        _check(load().dasp_inverse_order(self._h, C.byref(p)), "dasp_inverse_order")
+        return p.value or 0
 
     def unpermute_to(self, d_y_perm, dests, row_offset: int, d_norm2=None, stream: int = 0) -> None:
         """Permuted slab product -> original order, scaled by 1/sqrt(*d_norm2), coalesced stores into every vector of

@@ -54,7 +54,9 @@ typedef enum {
 typedef enum {
     DASP_VARIANT_AUTO = 0,
     DASP_VARIANT_CUDA_CORE = 1, /* per-lane 4-wide dot over the 8x4 tiles, 256/128-bit loads */
-    DASP_VARIANT_MMA = 2,       /* mma.sync m8n8k4.f64 (DMMA) on the same tiles, as the reference does */
+    DASP_VARIANT_MMA = 2,       /* tensor cores on the same tiles: FP64 mma.sync m8n8k4 (DMMA) as the reference does;
+                                   FP16 mma.sync m16n8k16 f16 x f16 -> f32 (HMMA.16816.F32; the reference's m8n8k4.f16 is
+                                   only emulated on sm_100a), medium and long rows */
     DASP_VARIANT_SPLIT = 3,     /* medium rows only: CUDA-core, four lanes per row (small, latency-bound matrices) */
     DASP_VARIANT_TMA = 4,       /* long rows only: CUDA-core fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier ring) */
     DASP_VARIANT_BLOCKED = 5    /* long rows only: column-blocked copy of the long part, x blocks staged in shared memory by
@@ -163,7 +165,7 @@ int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t 
                 int64_t *bytes);
 
 /* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA
- * (FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
+ * (short-row MMA is FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 
 /* The medium-row kernels read a compact resident copy of the regular part's column indices (per 8x4 tile one
@@ -203,6 +205,24 @@ int dasp_spmv_all_f16(const char *filename, const void *csrValA, const int *csrR
  * all-reduce of the next norm) before the vectors are read.  FP64 and FP16. */
 int dasp_spmv_scatter_to(dasp_handle *h, const void *d_x, void *const *d_dests, int n_dests, int64_t row_offset,
                          const double *d_norm2, void *stream);
+
+/* The same fused product + exchange with the slab product left in PERMUTED order (no scatter: the stores of
+ * neighbouring rows are contiguous): y_perm[k] / sqrt(*d_norm2) is stored at element row_offset + k of every vector in
+ * d_dests.  Meant for the relabelled mode below, where the permuted product IS the next x. */
+int dasp_spmv_permuted_to(dasp_handle *h, const void *d_x, void *const *d_dests, int n_dests, int64_t row_offset,
+                          const double *d_norm2, void *stream);
+
+/* Relabelled (P*A*P^T) mode for solvers that feed y back as the next x: the kernels' column indices
+ * are replaced by d_new_index[column] (device array of n ints with values in [0, n_new)), so x is expected in the
+ * relabelled index space (length n_new).  With d_new_index = the inverse permutation (dasp_inverse_order) of a square
+ * matrix, x is expected in PERMUTED order — exactly the order dasp_spmv produces y in — and the iteration needs neither
+ * dasp_spmv_unpermuted's scattered stores nor an un-permute pass; with row slabs on several GPUs, d_new_index[j] =
+ * slab offset of the owner of row j + that slab's inverse permutation of j.  The reference arrays (dasp_export) are
+ * untouched; compact indices and the column-blocked copy of the long part are rebuilt.  Synchronous; no product of the
+ * handle may be in flight.  May be called again with another map (always relative to the ORIGINAL column indices). */
+int dasp_relabel_columns(dasp_handle *h, const int *d_new_index, int n_new);
+/* device pointer to the inverse of order_rid: original row -> permuted index, int[m] */
+int dasp_inverse_order(const dasp_handle *h, const int **d_inv_order);
 
 /* The exchange step of the iterated workload as ONE coalesced pass: y (this GPU's slab product in PERMUTED order, as
  * dasp_spmv leaves it) is read through the inverse permutation, scaled by 1/sqrt(*d_norm2) when d_norm2 != NULL and

@@ -67,7 +67,8 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         tdt = torch.float16 if dtype == oracle.F16 else torch.float64
         dx = torch.from_numpy(x).to(cuda_device)
         for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED]
-                        if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED]):
+                        if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA,
+                                                     dasp.VARIANT_BLOCKED]):  # FP16 MMA = HMMA m16n8k16 (medium and long rows)
             # medium: cuda/mma/split; long: cuda/mma/tma/blocked; short: cuda/mma (a variant that does not apply = cuda-core)
             h.set_variant(variant if variant not in (dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED) else dasp.VARIANT_CUDA_CORE,
                           variant if variant != dasp.VARIANT_SPLIT else dasp.VARIANT_CUDA_CORE,

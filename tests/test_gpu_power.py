@@ -145,3 +145,89 @@ def test_two_handles_on_two_streams_interleaved(cuda_device):
         assert abs(n2[i].item() - float(np.dot(y_ref, y_ref))) <= 1e-11 * float(np.dot(y_ref, y_ref))
     for h in hs:
         h.close()
+
+
+@pytest.mark.parametrize("name", ["mixed_f1", "symmetric_like", "powerlaw_20k_square"])
+@pytest.mark.parametrize("long_variant", ["chunked", "blocked"])
+def test_relabelled_mode_equals_the_plain_product(cuda_device, name, long_variant):
+    """P*A*P^T mode (dasp_relabel_columns with the inverse permutation): x given in PERMUTED order, y produced in permuted
+    order; equals the plain product through order_rid, and a power iteration that feeds y_perm straight back as x
+    (dasp_spmv_permuted_to, no scatter, no un-permute pass) reproduces the eigenvalue estimate and the iterate of the
+    unpermuted path.  Two slabs with a global relabelling reproduce the single-handle product."""
+    import torch
+
+    import dasp_b200
+    import matrices
+
+    if name == "powerlaw_20k_square":
+        m, n, rp, ci, v = matrices.powerlaw(m=20000, lmax=5000)
+    else:
+        m, n, rp, ci, v = get(name)
+    if m != n:  # square it: columns folded into [0, m)
+        ci = (ci % m).astype(np.int32)
+        n = m
+    lv = dasp_b200.VARIANT_BLOCKED if long_variant == "blocked" else dasp_b200.VARIANT_CUDA_CORE
+    s = torch.cuda.current_stream().cuda_stream
+    x0 = x_for(n)
+    y_ref = oracle.csr_spmv_f64(m, rp, ci, v, x0)
+    h = dasp_b200.Dasp(dasp_b200.DASP_F64, m, n, rp, ci, v)
+    h.set_variant(0, lv, 0)
+    order = h.export("order_rid")
+    inv = np.empty(m, dtype=np.int32)
+    inv[order] = np.arange(m, dtype=np.int32)
+    d_inv = torch.from_numpy(inv).to(cuda_device)
+    before = {a: h.export(a) for a in ("reg_cid", "long_cid", "short_cid", "irreg_cid")}
+    h.relabel_columns(d_inv, m)
+    for a, arr in before.items():  # the reference arrays are untouched by the relabelling
+        assert np.array_equal(h.export(a), arr), a
+    xp = torch.from_numpy(x0[order]).to(cuda_device)
+    yp = torch.full((m,), float("nan"), dtype=torch.float64, device=cuda_device)
+    for rep in range(2):
+        h.spmv(xp, yp, s)
+        torch.cuda.synchronize()
+        got = yp.cpu().numpy()
+        assert np.linalg.norm(got - y_ref[order]) <= 1e-12 * np.linalg.norm(y_ref), (name, rep)
+    # power iteration entirely in permuted space
+    xa, xb = xp.clone(), torch.zeros_like(xp)
+    nrm2 = [torch.ones(1, dtype=torch.float64, device=cuda_device), torch.ones(1, dtype=torch.float64, device=cuda_device)]
+    x_ref = x0.copy()
+    lam_ref = 0.0
+    for k in range(5):
+        # x_k is stored un-normalised; the product scales by 1/sqrt(||x_k||^2) read on the device
+        h.spmv_permuted_to(xa, [xb], 0, nrm2[k & 1], s)
+        dasp_b200.sumsq(xb, m, nrm2[(k + 1) & 1], s)
+        xa, xb = xb, xa
+        y = oracle.csr_spmv_f64(m, rp, ci, v, x_ref)
+        lam_ref = np.sqrt(np.dot(y, y))
+        x_ref = y / lam_ref
+    torch.cuda.synchronize()
+    lam = float(torch.sqrt(nrm2[5 & 1]).item())
+    assert abs(lam - lam_ref) <= 1e-11 * lam_ref
+    got = (xa / lam).cpu().numpy()
+    assert np.linalg.norm(got - x_ref[order]) <= 1e-11
+    h.close()
+
+    # two row slabs, global relabelling: new index of column j = slab offset of its owner + that slab's inverse order
+    cuts = dasp_b200.partition_rows(rp, 2)
+    hs, invs = [], []
+    for p in range(2):
+        r0, r1 = int(cuts[p]), int(cuts[p + 1])
+        rps = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+        hp = dasp_b200.Dasp(dasp_b200.DASP_F64, r1 - r0, n, rps, ci[rp[r0]:rp[r1]], v[rp[r0]:rp[r1]])
+        hp.set_variant(0, lv, 0)
+        o = hp.export("order_rid")
+        iv = np.empty(r1 - r0, dtype=np.int32)
+        iv[o] = np.arange(r1 - r0, dtype=np.int32)
+        hs.append((hp, o, r0, r1))
+        invs.append(iv + r0)
+    gmap = torch.from_numpy(np.concatenate(invs).astype(np.int32)).to(cuda_device)
+    gorder = np.concatenate([o + r0 for (_, o, r0, _) in hs])
+    xg = torch.from_numpy(x0[gorder]).to(cuda_device)
+    yg = torch.full((m,), float("nan"), dtype=torch.float64, device=cuda_device)
+    for hp, o, r0, r1 in hs:
+        hp.relabel_columns(gmap, m)
+        hp.spmv_permuted_to(xg, [yg], r0, None, s)
+    torch.cuda.synchronize()
+    assert np.linalg.norm(yg.cpu().numpy() - y_ref[gorder]) <= 1e-12 * np.linalg.norm(y_ref)
+    for hp, *_ in hs:
+        hp.close()
