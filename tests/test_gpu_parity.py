@@ -449,3 +449,34 @@ def test_fuzz_layout_and_product(dasp, cuda_device, seed):
         scale = max(np.linalg.norm(y_ref), 1e-300)
         assert np.linalg.norm(got - y_ref) / scale <= (FP64_TOL if dtype == oracle.F64 else 4e-3), f"seed {seed}"
         h.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "half"])
+def test_reference_main_linked_against_the_shim(cuda_device, tmp_path, prec):
+    """The reference's OWN main program (src/main_f64.cu / src/main_f16.cu, unmodified: its Matrix Market reader, its
+    cuSPARSE comparator, its spmv_all call site, its CSV append) built against libdasp_b200.so through
+    include/dasp_reference_shim.h (oracle/Makefile `ref`, symlink shadow directory), with the verification it left
+    commented out re-enabled: verify_new(cuSPARSE y, our y, our order_rid, rows) (src/main_f64.cu:3-16,157) must succeed."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", f"spmv_{prec}_shim")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/spmv_*_shim not built (needs /root/reference at build time)")
+    os.makedirs(tmp_path / "data")  # the reference appends its record to data/*.csv relative to the working directory
+    files = [os.path.join(root, "tests", "golden", "mtx", f) for f in ("general_real.mtx", "symmetric_real.mtx", "pattern_symmetric.mtx")]
+    m, n, rp, ci, v = get("mixed_f1")  # every row category, long rows included
+    big = tmp_path / "f1.mtx"
+    with open(big, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m, n, int(rp[m])))
+        for i in range(m):
+            for j in range(rp[i], rp[i + 1]):
+                f.write("%d %d %.17g\n" % (i + 1, ci[j] + 1, v[j]))
+    for path in files + [str(big)]:
+        p = subprocess.run([exe, path], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+        assert p.returncode == 0, (path, p.stdout[-800:], p.stderr[-800:])
+        assert "compute succeed" in p.stdout and "VERIFY_NEW rc=0" in p.stdout, p.stdout[-800:]
+        assert "cusparse:" in p.stdout
+    rec = open(tmp_path / "data" / ("spmv_f64_record.csv" if prec == "double" else "spmv_f16_record.csv")).read().strip().splitlines()
+    assert len(rec) == len(files) + 1
