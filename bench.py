@@ -480,7 +480,8 @@ def run_ours(args):
                                                "path": "dasp_spmv_host (H2D, kernel, D2H back to back, synchronous)"}},
         "preprocess": {"gpu_ms": st["preprocess_ms"], "create_wall_s": create_s, "rate_fill0": st["rate_fill0"],
                        "row_long": st["row_long"], "row_block": st["row_block"], "short_rows": st["short_row_1"] + 2 * st["common_13"] + st["short_row_34"] + st["short_row_2"],
-                       "device_bytes": st["device_bytes"]},
+                       "device_bytes": st["device_bytes"], "long_gather_lines": st["long_gather_lines"],
+                       "long_rows_column_blocked": bool(st["long_blocked"])},
         "parity_check_rel_l2": chk,
     }
     if breakdown:

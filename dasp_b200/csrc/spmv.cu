@@ -757,12 +757,13 @@ __device__ __forceinline__ void short_singles(const SpmvArgs &a, long w)
     }
 }
 
-// y index of tile T (8 tile rows), row r, half h inside a 1&3 or 2&2 segment:
-// FP64 interleaves per tile (G = 8), FP16 per group of 4 tiles (G = 32); K11 / P10 of SURVEY §8a
-__device__ __forceinline__ long paired_y(int G, long tile, int r, int h)
+// y index of tile `tile` (8 tile rows), row r, half h inside a 1&3 or 2&2 segment: FP64 interleaves per tile (G = 8 rows),
+// FP16 per group of 4 tiles (G = 32); K11 / P10 of SURVEY §8a.  G is a compile-time constant of the value type, so this
+// is shifts and adds (the run-time form cost two 64-bit divisions per tile: half of the short kernels' instructions).
+template <typename T> __device__ __forceinline__ int paired_y(int tile, int r, int h)
 {
-    const int tg = G >> 3;
-    return (tile / tg) * (2L * G) + (long)h * G + (tile % tg) * 8 + r;
+    if (sizeof(T) == 8) return tile * 16 + h * 8 + r;
+    return (tile >> 2) * 64 + h * 32 + (tile & 3) * 8 + r;
 }
 
 // MODE 0: 1&3 tiles   MODE 1: 3/4 rows   MODE 2: 2&2 tiles
@@ -775,20 +776,21 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     const T *x = static_cast<const T *>(a.x);
+    constexpr int G = sizeof(T) == 8 ? 8 : 32; // == a.G
     const int sbase = MODE == 0 ? a.s13 : (MODE == 1 ? a.s34 : a.s22);
-    const long nrows = MODE == 0 ? a.c13 : (MODE == 1 ? a.n34 : a.n2); // rows (pairs for MODE 0)
+    const int nrows = MODE == 0 ? a.c13 : (MODE == 1 ? a.n34 : a.n2); // rows (pairs for MODE 0)
     const T *val = static_cast<const T *>(a.short_val) + sbase;
     const int *cid = a.short_cid + sbase;
-    const long tile0 = w * SHORT_TILES_PER_WARP;
+    const int tile0 = (int)w * SHORT_TILES_PER_WARP;
     // 2&2 packs 2G rows per G/8 tiles (16 per tile in FP64, 64 per 4 tiles in FP16)
-    const long tiles_avail = MODE == 2 ? ((nrows + 2 * a.G - 1) / (2 * a.G)) * (a.G >> 3) : (nrows + 7) / 8;
+    const int tiles_avail = MODE == 2 ? (int)(((long)nrows + 2 * G - 1) / (2 * G)) * (G >> 3) : (nrows + 7) / 8;
     A p[SHORT_TILES_PER_WARP];
     T v[SHORT_TILES_PER_WARP];
     int c[SHORT_TILES_PER_WARP];
 #pragma unroll
     for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
         bool ok = tile0 + j < tiles_avail;
-        long s = (tile0 + j) * 32 + lane;
+        long s = (long)(tile0 + j) * 32 + lane;
         v[j] = ok ? ld_stream1(val + s, pol) : T(0);
         c[j] = ok ? ld_stream1(cid + s, pol) : 0;
     }
@@ -799,13 +801,13 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
         const bool holder = q == (r >> 1);
 #pragma unroll
         for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
-            const long tile = tile0 + j;
+            const int tile = tile0 + j;
             const double av = (double)to_acc(v[j]);
             const double xg = (double)gather(x, c[j]);
             double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
             if (MODE == 1) {
                 dmma884(c0, av, xg);
-                const long row = tile * 8 + r;
+                const int row = tile * 8 + r;
                 if (holder && row < nrows) store_y<T>(a, a.y34 + row, (A)c0[r & 1]);
             } else {
                 const bool first = MODE == 0 ? q == 0 : q < 2; // slots of the first row of the tile row
@@ -813,11 +815,11 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
                 dmma884(c1, av, first ? 0.0 : xg);
                 if (MODE == 0) {
                     if (holder && tile * 8 + r < nrows) {
-                        store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), (A)c0[r & 1]);
-                        store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), (A)c1[r & 1]);
+                        store_y<T>(a, a.y13 + paired_y<T>(tile, r, 0), (A)c0[r & 1]);
+                        store_y<T>(a, a.y13 + paired_y<T>(tile, r, 1), (A)c1[r & 1]);
                     }
                 } else if (holder) {
-                    const long y0 = paired_y(a.G, tile, r, 0), y1 = paired_y(a.G, tile, r, 1);
+                    const int y0 = paired_y<T>(tile, r, 0), y1 = paired_y<T>(tile, r, 1);
                     if (y0 < nrows) store_y<T>(a, a.y22 + y0, (A)c0[r & 1]);
                     if (y1 < nrows) store_y<T>(a, a.y22 + y1, (A)c1[r & 1]);
                 }
@@ -828,23 +830,23 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
         for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
 #pragma unroll
         for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
-            const long tile = tile0 + j;
+            const int tile = tile0 + j;
             if (MODE == 1) {
                 A s = p[j] + __shfl_xor_sync(0xffffffffu, p[j], 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
-                long row = tile * 8 + r;
+                int row = tile * 8 + r;
                 if (q == 0 && row < nrows) store_y<T>(a, a.y34 + row, s);
             } else if (MODE == 0) {
                 A d1 = __shfl_down_sync(0xffffffffu, p[j], 1), d2 = __shfl_down_sync(0xffffffffu, p[j], 2);
-                long pair = tile * 8 + r;
+                int pair = tile * 8 + r;
                 if (pair < nrows) {
-                    if (q == 0) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 0), p[j]);
-                    if (q == 1) store_y<T>(a, a.y13 + paired_y(a.G, tile, r, 1), p[j] + d1 + d2);
+                    if (q == 0) store_y<T>(a, a.y13 + paired_y<T>(tile, r, 0), p[j]);
+                    if (q == 1) store_y<T>(a, a.y13 + paired_y<T>(tile, r, 1), p[j] + d1 + d2);
                 }
             } else {
                 A d1 = __shfl_down_sync(0xffffffffu, p[j], 1);
                 if ((q & 1) == 0) {
-                    long yi = paired_y(a.G, tile, r, q >> 1);
+                    int yi = paired_y<T>(tile, r, q >> 1);
                     if (yi < nrows) store_y<T>(a, a.y22 + yi, p[j] + d1);
                 }
             }
@@ -978,7 +980,7 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
             int r[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                r[j] = (int)((unsigned)k[ok ? j : 3] >> 16); // past the end: the row of the slice's last entry
+                r[j] = (int)((unsigned)(ok ? k[j] : k[3]) >> 16); // past the end: the row of the slice's last entry
                 p[j] = ok ? to_acc(v[j]) * to_acc(xs[k[j] & 0xFFFF]) : A(0);
             }
             if (__all_sync(0xffffffffu, r[0] == cur && r[3] == cur)) { lane_acc += (p[0] + p[1]) + (p[2] + p[3]); return; }
@@ -1288,7 +1290,8 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     a.items[6] = on_zero * (long)cdiv(s.row_zero, 32);
     // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
     const bool keep = small && med != 1 && !mma_long && !tma_long && !mma_short;
-    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 128; // A/B aid: 256 = round-1 shape
+    // measured (profiles/r02): the 128-thread / 7-CTA form is SLOWER on C1 / C2 (17.9 vs 9.3 us, 12.2 vs 7.2 us): kept as an A/B aid
+    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 256;
     const bool narrow = keep && keep_shape == 128;
     const int nw = narrow ? 4 : WARPS;
     long total_items = 0;
