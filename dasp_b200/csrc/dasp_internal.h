@@ -109,6 +109,13 @@ struct Layout {
     unsigned char *long_wide = nullptr;     // [n_long_units] in execution order
     int *inv_order = nullptr;               // [m] inverse of order_rid (original row -> permuted index)
     unsigned char *med_has_irreg = nullptr; // [ceil(row_block/32)] 1 if any row of the 32-row group has an irregular tail
+    // Locality-ordered work lists (large matrices): the fused kernel walks the medium 32-row groups, and the CTAs of the four
+    // short segments interleaved, in order of the ORIGINAL id of their first row, so that at any time the resident CTAs
+    // gather from one sliding window of x (every length class / short segment sweeps all of x on its own otherwise).
+    int *med_order = nullptr;               // [blocknum / 4] group processed by the w-th medium warp
+    int *short_map = nullptr;               // [short_map_n] category << 28 | CTA index inside the category
+    int short_map_n = 0;
+    int short_ctas[4] = {0, 0, 0, 0};       // CTAs of singles / 1&3 / 3&4 / 2&2 the map was built for
     double long_lines_avg = 0.0;            // estimated distinct 128-byte lines of x per 32-slot group of the long part
     // Column-blocked copy of the long part ("LCB", built when the long rows gather x all over the place): the live
     // entries of all long rows sorted by (column block, long row); a CTA stages one block of x in shared memory with a
@@ -153,8 +160,11 @@ struct dasp_handle {
 };
 
 namespace dasp {
+constexpr int SPMV_CTA = 256;           // threads per CTA of the fused kernel (bandwidth-bound form)
+constexpr int SINGLES_PER_THREAD = 4;   // single-entry rows per thread
+constexpr int SHORT_TILES_PER_WARP = 4; // 8x4 tiles of a short segment per warp
 constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
-constexpr int LCB_PART = 32768;     // entries per CTA of the column-blocked long-row kernel (a multiple of 8 warps x 128)
+constexpr int LCB_PART = 65536;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
 
 // preprocess.cu

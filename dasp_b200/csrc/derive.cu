@@ -118,8 +118,11 @@ __global__ void compress_long_cid(const int *__restrict__ unit_row, const int *_
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
         if (mn == INT32_MAX) mn = 0;
-        // 128-byte lines of x one 32-lane gather of this group touches, estimated from its column span
-        nlines += (unsigned long long)min(32L, ((long)(mx - mn) * esz >> 7) + 1);
+        // 128-byte lines of x one 32-lane gather of this group touches: lanes whose line differs from their left
+        // neighbour's (exact for ascending columns, ~32 for scattered ones)
+        const int line = (int)(((long)c * esz) >> 7);
+        const int left = __shfl_up_sync(0xffffffffu, line, 1);
+        nlines += (unsigned long long)__popc(__ballot_sync(0xffffffffu, lane == 0 || line != left));
         const bool ok = (mx - mn) < 65535;
         any_wide |= !ok;
         cdelta[p + lane] = (unsigned short)(c == 0 ? 0xFFFF : (ok ? c - mn : 0));
@@ -129,6 +132,37 @@ __global__ void compress_long_cid(const int *__restrict__ unit_row, const int *_
     if (lane == 0 && nlines) atomicAdd(lines, nlines);
 }
 
+
+// ---- locality-ordered work lists ------------------------------------------------------------------------------
+__global__ void med_group_keys(const int *__restrict__ order_rid, int row_long, int row_block, int ngroups, int *__restrict__ key,
+                               int *__restrict__ val)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const long r = 32L * g;
+    key[g] = r < row_block ? order_rid[row_long + r] : INT32_MAX; // padding groups last
+    val[g] = g;
+}
+
+struct ShortOrderGeom {
+    int ctas[4];  // CTAs of singles, 1&3, 3&4, 2&2
+    int rows[4];  // y entries one CTA covers in each
+    int ybase[4]; // first permuted index of each segment
+    int count[4]; // y entries of each segment
+    int pair_group; // 8 (f64) / 32 (f16): one-rows of a 1&3 group precede its three-rows
+};
+// one key per short CTA: original id of the first row it produces
+__global__ void short_cta_keys(const int *__restrict__ order_rid, ShortOrderGeom g, int total, int *__restrict__ key, int *__restrict__ val)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = 0, local = i;
+    while (c < 3 && local >= g.ctas[c]) { local -= g.ctas[c]; c++; }
+    long first = (long)local * g.rows[c];
+    if (c == 1 && first + g.pair_group < g.count[c]) first += g.pair_group; // the 3-row of the first pair (3 of its 4 entries)
+    key[i] = first < g.count[c] ? order_rid[g.ybase[c] + first] : INT32_MAX;
+    val[i] = ((c + 2) << 28) | local;
+}
 
 // ---- LCB: column-blocked copy of the long part -----------------------------------------------------------------
 
@@ -498,6 +532,51 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
     if (cm > 0) flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
     DASP_TRY(derive_indices(h, st, lines));
+    // ---- locality-ordered work lists (see dasp_internal.h) ----
+    {
+        const int ngroups4 = blocknum / 4;
+        DASP_TRY(pool.alloc((void **)&L.med_order, sizeof(int) * (size_t)ngroups4));
+        if (ngroups4 > 0) {
+            int *k0 = nullptr, *v0 = nullptr, *k1 = nullptr;
+            DASP_TRY(tmp.alloc((void **)&k0, sizeof(int) * (size_t)ngroups4));
+            DASP_TRY(tmp.alloc((void **)&v0, sizeof(int) * (size_t)ngroups4));
+            DASP_TRY(tmp.alloc((void **)&k1, sizeof(int) * (size_t)ngroups4));
+            med_group_keys<<<grid_for(ngroups4, 256), 256, 0, st>>>(L.order_rid, cl, cm, ngroups4, k0, v0);
+            DASP_TRY(radix_sort_pairs(tmp, k0, v0, k1, L.med_order, ngroups4, 31, false, st));
+        }
+        const int f16 = h->dtype == DASP_F16;
+        const int G = f16 ? 32 : 8, warps = SPMV_CTA / 32;
+        const int tiles13 = ceil_div(s.common_13, 8), tiles34 = ceil_div(s.short_row_34, 8);
+        const int tiles22 = ceil_div(s.short_row_2, 2 * G) * (G / 8);
+        ShortOrderGeom g;
+        g.ctas[0] = ceil_div(ceil_div(s.short_row_1, 32 * SINGLES_PER_THREAD), warps);
+        g.ctas[1] = ceil_div(ceil_div(tiles13, SHORT_TILES_PER_WARP), warps);
+        g.ctas[2] = ceil_div(ceil_div(tiles34, SHORT_TILES_PER_WARP), warps);
+        g.ctas[3] = ceil_div(ceil_div(tiles22, SHORT_TILES_PER_WARP), warps);
+        g.rows[0] = warps * 32 * SINGLES_PER_THREAD;
+        g.rows[1] = warps * SHORT_TILES_PER_WARP * 16; // 8 pairs = 16 y entries per tile
+        g.rows[2] = warps * SHORT_TILES_PER_WARP * 8;
+        g.rows[3] = warps * SHORT_TILES_PER_WARP * 16;
+        const int ybase = cl + cm; // K11 placement (see launch_spmv)
+        g.ybase[1] = ybase + (f16 ? 0 : s.short_row_1);
+        g.ybase[2] = g.ybase[1] + 2 * s.common_13;
+        g.ybase[3] = g.ybase[2] + s.short_row_34;
+        g.ybase[0] = f16 ? g.ybase[3] + s.short_row_2 : ybase;
+        g.pair_group = G;
+        g.count[0] = s.short_row_1; g.count[1] = 2 * s.common_13; g.count[2] = s.short_row_34; g.count[3] = s.short_row_2;
+        const int total = g.ctas[0] + g.ctas[1] + g.ctas[2] + g.ctas[3];
+        L.short_map_n = total;
+        for (int c = 0; c < 4; c++) L.short_ctas[c] = g.ctas[c];
+        DASP_TRY(pool.alloc((void **)&L.short_map, sizeof(int) * (size_t)total));
+        if (total > 0) {
+            int *k0 = nullptr, *v0 = nullptr, *k1 = nullptr;
+            DASP_TRY(tmp.alloc((void **)&k0, sizeof(int) * (size_t)total));
+            DASP_TRY(tmp.alloc((void **)&v0, sizeof(int) * (size_t)total));
+            DASP_TRY(tmp.alloc((void **)&k1, sizeof(int) * (size_t)total));
+            short_cta_keys<<<grid_for(total, 256), 256, 0, st>>>(L.order_rid, g, total, k0, v0);
+            DASP_TRY(radix_sort_pairs(tmp, k0, v0, k1, L.short_map, total, 31, false, st));
+        }
+    }
     // ---- inverse permutation (dasp_unpermute_to, relabelled mode) ----
     DASP_TRY(pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
     if (m > 0) invert_order<<<grid_for(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);

@@ -31,10 +31,8 @@
 namespace dasp {
 namespace {
 
-constexpr int CTA = 256;
+constexpr int CTA = SPMV_CTA;
 constexpr int WARPS = CTA / 32;
-constexpr int SINGLES_PER_THREAD = 4;
-constexpr int SHORT_TILES_PER_WARP = 4;
 #ifndef MED_TB
 #define MED_TB 4 // tiles per batch of the large-matrix medium kernel (compact-index path)
 #endif
@@ -73,6 +71,8 @@ struct SpmvArgs {
     const unsigned short *reg_cdelta; //                  per-slot 16-bit offset, 0xFFFF = column 0
     const unsigned char *blk_wide;    // nullptr: compression off; else 1 = block reads reg_cid
     const unsigned short *blk_live;   // tiles of the block worth reading (trailing all-zero tiles dropped)
+    const int *med_order;             // locality order of the 32-row groups (nullptr: identity)
+    const int *short_map;             // locality order of the short CTAs: category << 28 | CTA inside it (nullptr: off)
     int row_long, row_block, blocknum;
     // short
     const void *short_val;
@@ -447,7 +447,8 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     if (w * 4 >= a.blocknum) return;
-    const int group = (int)w; // 32 rows = 4 blocks
+    // 32 rows = 4 blocks; large matrices walk the groups in order of the original id of their first row
+    const int group = (!KEEP && !MMA && a.med_order) ? __ldg(a.med_order + w) : (int)w;
     const T *x = static_cast<const T *>(a.x);
     const T *val = static_cast<const T *>(a.reg_val);
     const int g = group * 32 + lane;
@@ -894,7 +895,14 @@ __global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spm
 #pragma unroll
     for (int k = 0; k < 6; k++)
         if (bid >= a.e[k]) { cat = k + 1; first = a.e[k]; }
-    const int local = bid - first;
+    int local = bid - first;
+    if constexpr (!KEEP) {
+        if (a.short_map && cat >= 2 && cat <= 5) { // the four short segments interleaved by row band
+            const int e = __ldg(a.short_map + (bid - a.e[1]));
+            cat = e >> 28;
+            local = e & 0x0FFFFFFF;
+        }
+    }
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
     if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
     run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * (NT / 32) + warp, dyn_smem);
@@ -952,16 +960,19 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     for (int i = (int)(bytes16 / sizeof(T)) + tid; i < cnt; i += CTA) xs[i] = xg[i]; // tail that is not a 16-byte multiple
 
     const int p0 = __ldg(a.lcb_blk_ptr + b), p1 = __ldg(a.lcb_blk_ptr + b + 1); // multiples of 4
-    const int beg = p0 + (c - __ldg(a.lcb_cta_first + b)) * LCB_PART, end = min(beg + LCB_PART, p1);
+    // the block's entries are cut into equal parts (multiples of 1024) for its CTAs
+    const int c0 = __ldg(a.lcb_cta_first + b), nparts = __ldg(a.lcb_cta_first + b + 1) - c0;
+    const int psize = (((p1 - p0 + nparts - 1) / nparts) + 1023) & ~1023;
+    const int beg = min(p0 + (c - c0) * psize, p1), end = min(beg + psize, p1);
     const int per = ((end - beg + WARPS * 128 - 1) / (WARPS * 128)) * 128;
     const int wbeg = beg + warp * per, wend = min(wbeg + per, end);
     const T *val = static_cast<const T *>(a.lcb_val);
     const StreamPol pol = make_stream_policy<false>();
     A *acc = static_cast<A *>(a.lcb_acc);
     if (wbeg < wend) {
-        T v0[4], v1[4];
-        int k0[4], k1[4];
-        bool ok0, ok1;
+        T v0[4], v1[4], v2[4];
+        int k0[4], k1[4], k2[4];
+        bool ok0, ok1, ok2;
         // a lane past the end of the slice re-reads the indices of the slice's last four entries (rows stay ascending)
         // and takes zeros as values
         auto load = [&](T(&v)[4], int(&k)[4], bool &ok, int i) {
@@ -1010,15 +1021,20 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
             lane_acc = (last_row == new_cur) ? ((split || r[0] != cur) ? last : A(0)) : A(0);
             cur = new_cur;
         };
+        // three steps (3 x 128 entries per warp) in flight: the kernel is bound by DRAM latency x bytes in flight
         load(v0, k0, ok0, wbeg);
+        load(v1, k1, ok1, wbeg + 128);
         mbar_wait(bar_addr, 0);
         __syncthreads(); // the tail elements written with plain stores
-        for (int i = wbeg; i < wend; i += 256) {
-            load(v1, k1, ok1, i + 128);
+        for (int i = wbeg; i < wend; i += 384) {
+            load(v2, k2, ok2, i + 256);
             consume(v0, k0, ok0);
             if (i + 128 >= wend) break;
-            load(v0, k0, ok0, i + 256);
+            load(v0, k0, ok0, i + 384);
             consume(v1, k1, ok1);
+            if (i + 256 >= wend) break;
+            load(v1, k1, ok1, i + 512);
+            consume(v2, k2, ok2);
         }
         if (cur >= 0) {
             const A total = warp_sum(lane_acc);
@@ -1303,6 +1319,15 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     }
     if (total_items == 0) return DASP_OK;
     const int grid = a.e[6];
+    // locality-ordered work lists: large matrices, everything on, the CTA counts the lists were built for
+    static const int use_order = getenv("DASP_NO_LOCALITY_ORDER") ? 0 : 1; // A/B aid
+    if (!keep && use_order) {
+        if (med == 0 && on_med) a.med_order = L.med_order;
+        const int c2 = a.e[2] - a.e[1], c3 = a.e[3] - a.e[2], c4 = a.e[4] - a.e[3], c5 = a.e[5] - a.e[4];
+        if (on_short && !mma_short && L.short_map_n > 0 && c2 == L.short_ctas[0] && c3 == L.short_ctas[1] && c4 == L.short_ctas[2] &&
+            c5 == L.short_ctas[3])
+            a.short_map = L.short_map;
+    }
 
     // the kernels that use no shared memory ask for the whole unified array as L1 (x gathers live there), as the
     // reference does (src/dasp_f64.h:1280-1283)

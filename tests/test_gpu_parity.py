@@ -469,7 +469,8 @@ def test_reference_main_linked_against_the_shim(cuda_device, tmp_path, prec):
     m, n, rp, ci, v = get("mixed_f1")  # every row category, long rows included
     big = tmp_path / "f1.mtx"
     with open(big, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m, n, int(rp[m])))
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write("%d %d %d\n" % (m, n, int(rp[m])))
         for i in range(m):
             for j in range(rp[i], rp[i + 1]):
                 f.write("%d %d %.17g\n" % (i + 1, ci[j] + 1, v[j]))
