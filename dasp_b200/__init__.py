@@ -7,9 +7,9 @@ tests and the benchmark driver; it mirrors the reference's single entry point ``
 :class:`Dasp`.  There is no CPU fallback: importing works without a GPU (so the symbol table can
 be checked), every compute call fails loudly without one.
 """
-from .lib import (DASP_F16, DASP_F64, VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA, VARIANT_BLOCKED, Dasp, DaspError,
+from .lib import (DASP_F16, DASP_F64, VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA, VARIANT_BLOCKED, VARIANT_BANDED, Dasp, DaspError,
                   build, exported_symbols, library_path, load, partition_rows, read_mtx, scale_copy_to, scale_rsqrt, spmv_all, sumsq)
 
-__all__ = ["DASP_F16", "DASP_F64", "VARIANT_AUTO", "VARIANT_CUDA_CORE", "VARIANT_MMA", "VARIANT_SPLIT", "VARIANT_TMA", "VARIANT_BLOCKED", "Dasp",
+__all__ = ["DASP_F16", "DASP_F64", "VARIANT_AUTO", "VARIANT_CUDA_CORE", "VARIANT_MMA", "VARIANT_SPLIT", "VARIANT_TMA", "VARIANT_BLOCKED", "VARIANT_BANDED", "Dasp",
            "DaspError", "build", "exported_symbols", "library_path", "load", "partition_rows",
            "read_mtx", "scale_copy_to", "scale_rsqrt", "spmv_all", "sumsq"]

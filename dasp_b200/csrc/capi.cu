@@ -560,6 +560,10 @@ int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows
         DASP_ON_DEVICE(h->device);
         DASP_TRY(build_lcb(h, h->own_stream));
     }
+    if (short_rows == DASP_VARIANT_BANDED && !h->L.sb_item) { // and the short-band work list
+        DASP_ON_DEVICE(h->device);
+        DASP_TRY(build_short_bands(h, h->own_stream, true));
+    }
     return DASP_OK;
 }
 

@@ -116,6 +116,13 @@ struct Layout {
     int *short_map = nullptr;               // [short_map_n] category << 28 | CTA index inside the category
     int short_map_n = 0;
     int short_ctas[4] = {0, 0, 0, 0};       // CTAs of singles / 1&3 / 3&4 / 2&2 the map was built for
+    // Short-band kernel: warp items of the four short segments sorted by the band of original rows they start in, and the
+    // x window of every band
+    int *sb_item = nullptr;                 // [sb_nitems] segment (2..5) << 28 | warp item inside the segment
+    int *sb_band_ptr = nullptr;             // [sb_nbands + 1]
+    int *sb_lo = nullptr;                   // [sb_nbands] first column of the band's window (multiple of 8)
+    int sb_nbands = 0, sb_nitems = 0, sb_auto = 0;
+    double sb_hit_rate = 0.0;               // fraction of short-row entries whose column lies inside its band's window
     double long_lines_avg = 0.0;            // estimated distinct 128-byte lines of x per 32-slot group of the long part
     // Column-blocked copy of the long part ("LCB", built when the long rows gather x all over the place): the live
     // entries of all long rows sorted by (column block, long row); a CTA stages one block of x in shared memory with a
@@ -136,6 +143,7 @@ struct Layout {
 
 struct dasp_handle {
     int device = 0;
+    int sb_attr_set = 0;
     int lcb_attr_set = 0; // lcb_kernel dynamic shared memory attribute set on this device
     int lcb_auto = 0; // AUTO uses the column-blocked long-row kernel (decided in derive() from long_lines_avg)
     dasp_dtype dtype = DASP_F64;
@@ -164,8 +172,10 @@ constexpr int SPMV_CTA = 256;           // threads per CTA of the fused kernel (
 constexpr int SINGLES_PER_THREAD = 4;   // single-entry rows per thread
 constexpr int SHORT_TILES_PER_WARP = 4; // 8x4 tiles of a short segment per warp
 constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
-constexpr int LCB_PART = 65536;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
+constexpr int LCB_PART = 32768;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
+constexpr int SB_BAND_ROWS = 4096;  // original rows per band of the short-band kernel
+constexpr int SB_WINDOW_BYTES = 98304; // bytes of x one band stages in shared memory (must match spmv.cu SB_WIN_BYTES)
 
 // preprocess.cu
 int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st);
@@ -174,6 +184,7 @@ int radix_sort_pairs(DevicePool &tmp, const int *keys_in, const int *vals_in, in
 // derive.cu: kernel-facing data derived from the reference layout (also after dasp_load); build_lcb on demand
 int derive(dasp_handle *h, cudaStream_t st);
 int build_lcb(dasp_handle *h, cudaStream_t st);
+int build_short_bands(dasp_handle *h, cudaStream_t st, bool force);
 // kernel-facing column indices := new_index[reference column]; compact indices and the column-blocked copy are rebuilt
 int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStream_t st);
 // range / monotonicity check of the offset and index arrays of a layout read from a file (dasp_load)

@@ -4,6 +4,9 @@
 // scattered over x — a column-blocked copy of the long part (LCB) whose kernel stages x in shared memory with TMA.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "dasp_internal.h"
 
 namespace dasp {
@@ -144,6 +147,17 @@ __global__ void med_group_keys(const int *__restrict__ order_rid, int row_long, 
     val[g] = g;
 }
 
+// positions where the identity order of the groups steps DOWN in original row id: out[0] = count, out[1..] = positions
+__global__ void med_descents(const int *__restrict__ key, int ngroups, int *__restrict__ out)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < 1 || g >= ngroups) return;
+    if (key[g] < key[g - 1]) {
+        const int slot = atomicAdd(out, 1);
+        if (slot < 4096) out[1 + slot] = g;
+    }
+}
+
 struct ShortOrderGeom {
     int ctas[4];  // CTAs of singles, 1&3, 3&4, 2&2
     int rows[4];  // y entries one CTA covers in each
@@ -162,6 +176,96 @@ __global__ void short_cta_keys(const int *__restrict__ order_rid, ShortOrderGeom
     if (c == 1 && first + g.pair_group < g.count[c]) first += g.pair_group; // the 3-row of the first pair (3 of its 4 entries)
     key[i] = first < g.count[c] ? order_rid[g.ybase[c] + first] : INT32_MAX;
     val[i] = ((c + 2) << 28) | local;
+}
+
+// ---- short-band kernel: warp items of the short segments by row band, x window per band --------------------------
+struct SbGeom {
+    int items[4];   // warp items of singles, 1&3, 3&4, 2&2 (as the fused kernel counts them)
+    int yrows[4];   // y entries one item covers
+    int ybase[4], count[4];
+    int sbase[4];   // first slot of each segment in short_val / short_cid
+    int slots[4];   // slots one item covers
+    int nslots[4];  // slots of the segment that exist
+    int pair_group;
+    int nbands, band_rows;
+};
+__device__ __forceinline__ int sb_locate(const SbGeom &g, int i, int &local)
+{
+    int c = 0;
+    local = i;
+    while (c < 3 && local >= g.items[c]) { local -= g.items[c]; c++; }
+    return c;
+}
+// key = band of the original row the item starts with
+__global__ void sb_item_keys(const int *__restrict__ order_rid, SbGeom g, int total, int *__restrict__ key, int *__restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int local;
+    const int c = sb_locate(g, i, local);
+    long first = (long)local * g.yrows[c];
+    if (c == 1 && first + g.pair_group < g.count[c]) first += g.pair_group;
+    key[i] = first < g.count[c] ? order_rid[g.ybase[c] + first] / g.band_rows : g.nbands;
+    val[i] = ((c + 2) << 28) | local;
+}
+// smallest column of every band (padding slots, value 0 and column 0, ignored): one warp per item
+template <typename T>
+__global__ void sb_min_col(const int *__restrict__ sorted_item, const int *__restrict__ sorted_band, int nitems, SbGeom g,
+                           const T *__restrict__ short_val, const int *__restrict__ short_cid, int *__restrict__ lo)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= nitems) return;
+    const int e = sorted_item[i], c = (e >> 28) - 2, local = e & 0x0FFFFFFF;
+    const long s0 = (long)local * g.slots[c];
+    int mn = INT32_MAX;
+    for (int k = lane; k < g.slots[c]; k += 32) {
+        const long p = s0 + k;
+        if (p < g.nslots[c]) {
+            const int col = short_cid[g.sbase[c] + p];
+            if (!(col == 0 && short_val[g.sbase[c] + p] == T(0))) mn = min(mn, col);
+        }
+    }
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0 && mn != INT32_MAX) atomicMin(lo + sorted_band[i], mn);
+}
+// window start of every band: the smallest column, but not left of (diagonal position of the band - half a window), so that
+// a few outlying columns cannot drag the window away from where the band's entries are; multiple of 8
+__global__ void sb_place_windows(int *__restrict__ lo, int nbands, int band_rows, int m, int n, int wcap)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbands) return;
+    const long centre = (long)(((double)b * band_rows + band_rows / 2) * (double)n / (double)(m > 0 ? m : 1));
+    long v = lo[b] == INT32_MAX ? 0 : lo[b];
+    v = max(v, centre - wcap / 2);
+    v = min(v, (long)max(0, n - 1));
+    lo[b] = (int)(v & ~7L);
+}
+__global__ void sb_fix_unset(int *__restrict__ lo, int n)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n && lo[b] == 0x7f7f7f7f) lo[b] = INT32_MAX;
+}
+// entries inside / outside their band's window
+template <typename T>
+__global__ void sb_hits(const int *__restrict__ sorted_item, const int *__restrict__ sorted_band, int nitems, SbGeom g,
+                        const T *__restrict__ short_val, const int *__restrict__ short_cid, const int *__restrict__ lo, int wcap,
+                        unsigned long long *__restrict__ counts)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= nitems) return;
+    const int e = sorted_item[i], c = (e >> 28) - 2, local = e & 0x0FFFFFFF;
+    const long s0 = (long)local * g.slots[c];
+    const int wlo = lo[sorted_band[i]];
+    int in = 0, all = 0;
+    for (int k = lane; k < g.slots[c]; k += 32) {
+        const long p = s0 + k;
+        if (p < g.nslots[c]) {
+            const int col = short_cid[g.sbase[c] + p];
+            if (!(col == 0 && short_val[g.sbase[c] + p] == T(0))) { all++; in += (unsigned)(col - wlo) < (unsigned)wcap; }
+        }
+    }
+    for (int o = 16; o; o >>= 1) { in += __shfl_xor_sync(0xffffffffu, in, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+    if (lane == 0) { atomicAdd(counts, (unsigned long long)in); atomicAdd(counts + 1, (unsigned long long)all); }
 }
 
 // ---- LCB: column-blocked copy of the long part -----------------------------------------------------------------
@@ -375,6 +479,85 @@ __global__ void map_cid(const int *__restrict__ src, const T *__restrict__ val, 
     }
 }
 
+// (re)build the short-band work list and windows from the kernel-facing short column indices
+template <typename T> int build_short_bands_t(dasp_handle *h, cudaStream_t st, bool force)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    DevicePool &pool = h->pool;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    if (L.sb_item) { pool.release(L.sb_item); pool.release(L.sb_band_ptr); pool.release(L.sb_lo); }
+    L.sb_item = nullptr; L.sb_band_ptr = nullptr; L.sb_lo = nullptr; L.sb_nbands = 0; L.sb_nitems = 0; L.sb_auto = 0; L.sb_hit_rate = 0.0;
+    const long short_rows = (long)s.short_row_1 + 2L * s.common_13 + s.short_row_34 + s.short_row_2;
+    if ((!force && short_rows < (1 << 20)) || short_rows == 0 || s.m <= 0) return DASP_OK; // small short parts stay in the fused kernel
+    const int f16 = h->dtype == DASP_F16, G = f16 ? 32 : 8;
+    const int tiles13 = ceil_div(s.common_13, 8), tiles34 = ceil_div(s.short_row_34, 8);
+    const int tiles22 = ceil_div(s.short_row_2, 2 * G) * (G / 8);
+    SbGeom g;
+    g.items[0] = ceil_div(s.short_row_1, 32 * SINGLES_PER_THREAD);
+    g.items[1] = ceil_div(tiles13, SHORT_TILES_PER_WARP);
+    g.items[2] = ceil_div(tiles34, SHORT_TILES_PER_WARP);
+    g.items[3] = ceil_div(tiles22, SHORT_TILES_PER_WARP);
+    g.yrows[0] = 32 * SINGLES_PER_THREAD; g.yrows[1] = SHORT_TILES_PER_WARP * 16; g.yrows[2] = SHORT_TILES_PER_WARP * 8;
+    g.yrows[3] = SHORT_TILES_PER_WARP * 16;
+    const int ybase = s.row_long + s.row_block;
+    g.ybase[1] = ybase + (f16 ? 0 : s.short_row_1);
+    g.ybase[2] = g.ybase[1] + 2 * s.common_13;
+    g.ybase[3] = g.ybase[2] + s.short_row_34;
+    g.ybase[0] = f16 ? g.ybase[3] + s.short_row_2 : ybase;
+    g.count[0] = s.short_row_1; g.count[1] = 2 * s.common_13; g.count[2] = s.short_row_34; g.count[3] = s.short_row_2;
+    const int f13 = s.fill0_nnz_short13, f34 = s.fill0_nnz_short34, f22 = s.fill0_nnz_short22;
+    g.sbase[0] = f16 ? f13 + f34 + f22 : 0;
+    g.sbase[1] = f16 ? 0 : s.short_row_1;
+    g.sbase[2] = g.sbase[1] + f13;
+    g.sbase[3] = g.sbase[2] + f34;
+    g.slots[0] = 32 * SINGLES_PER_THREAD; g.slots[1] = g.slots[2] = g.slots[3] = SHORT_TILES_PER_WARP * 32;
+    g.nslots[0] = s.short_row_1; g.nslots[1] = f13; g.nslots[2] = f34; g.nslots[3] = f22;
+    g.pair_group = G;
+    g.band_rows = SB_BAND_ROWS;
+    g.nbands = ceil_div(s.m, SB_BAND_ROWS);
+    const int total = g.items[0] + g.items[1] + g.items[2] + g.items[3];
+    if (total <= 0) return DASP_OK;
+    int *k0 = nullptr, *v0 = nullptr, *k1 = nullptr;
+    DASP_TRY(tmp.alloc((void **)&k0, sizeof(int) * (size_t)total));
+    DASP_TRY(tmp.alloc((void **)&v0, sizeof(int) * (size_t)total));
+    DASP_TRY(tmp.alloc((void **)&k1, sizeof(int) * (size_t)total));
+    DASP_TRY(pool.alloc((void **)&L.sb_item, sizeof(int) * (size_t)total));
+    DASP_TRY(pool.alloc((void **)&L.sb_band_ptr, sizeof(int) * (size_t)(g.nbands + 2)));
+    DASP_TRY(pool.alloc((void **)&L.sb_lo, sizeof(int) * (size_t)(g.nbands + 1)));
+    sb_item_keys<<<grid_for(total, 256), 256, 0, st>>>(L.order_rid, g, total, k0, v0);
+    int bits = 1;
+    while ((1 << bits) <= g.nbands) bits++;
+    DASP_TRY(radix_sort_pairs(tmp, k0, v0, k1, L.sb_item, total, bits, false, st));
+    lcb_block_ptr<<<grid_for(g.nbands + 2, 256), 256, 0, st>>>(k1, total, g.nbands + 1, L.sb_band_ptr); // lower bounds of 0..nbands+1
+    DASP_CUDA(cudaMemsetAsync(L.sb_lo, 0x7f, sizeof(int) * (size_t)(g.nbands + 1), st)); // 0x7f7f7f7f: "no entry yet"
+    int nitems = 0;
+    DASP_CUDA(cudaMemcpyAsync(&nitems, L.sb_band_ptr + g.nbands, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    const int wcap = SB_WINDOW_BYTES / (int)sizeof(T);
+    const T *sval = (const T *)L.short_val;
+    unsigned long long *counts = nullptr, hc[2] = {0, 0};
+    DASP_TRY(tmp.alloc((void **)&counts, sizeof(unsigned long long) * 2));
+    DASP_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 2, st));
+    if (nitems > 0) {
+        sb_min_col<T><<<grid_for((long)nitems * 32, 256), 256, 0, st>>>(L.sb_item, k1, nitems, g, sval, L.k_short_cid, L.sb_lo);
+        sb_fix_unset<<<grid_for(g.nbands + 1, 256), 256, 0, st>>>(L.sb_lo, g.nbands + 1);
+        sb_place_windows<<<grid_for(g.nbands, 256), 256, 0, st>>>(L.sb_lo, g.nbands, SB_BAND_ROWS, s.m, L.x_len, wcap);
+        sb_hits<T><<<grid_for((long)nitems * 32, 256), 256, 0, st>>>(L.sb_item, k1, nitems, g, sval, L.k_short_cid, L.sb_lo, wcap, counts);
+    }
+    DASP_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    DASP_CUDA(cudaGetLastError());
+    L.sb_nbands = g.nbands; L.sb_nitems = nitems;
+    L.sb_hit_rate = hc[1] ? (double)hc[0] / (double)hc[1] : 0.0;
+    // worth it when nearly every gather is served from the window (measured crossover: profiles/r02/README.md)
+    L.sb_auto = nitems > 0 && L.sb_hit_rate >= 0.8;
+    L.s.short_band_hit_rate = L.sb_hit_rate;
+    L.s.short_banded = L.sb_auto;
+    return DASP_OK;
+}
+
 // compact forms of the kernel-facing column indices (and the estimate that decides chunked vs column-blocked long rows)
 int derive_indices(dasp_handle *h, cudaStream_t st, unsigned long long *lines)
 {
@@ -414,7 +597,7 @@ int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long lon
         DASP_CUDA(cudaStreamSynchronize(st));
         L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
         L.s.long_gather_lines = L.long_lines_avg;
-        double thr = 12.0; // measured crossover, profiles/r02/README.md
+        double thr = 20.0; // measured crossover (profiles/r02/README.md): 12.5 lines -> chunked wins, 31.7 -> column-blocked wins
         if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
         if (L.long_lines_avg > thr && s.row_long <= 65535 && s.nnz_long >= 4 * LCB_PART) {
             DASP_TRY(build_lcb(h, st));
@@ -426,6 +609,13 @@ int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long lon
 }
 
 } // namespace
+
+int build_short_bands(dasp_handle *h, cudaStream_t st, bool force)
+{
+    int rc = h->dtype == DASP_F16 ? build_short_bands_t<unsigned short>(h, st, force) : build_short_bands_t<double>(h, st, force);
+    h->L.s.device_bytes = h->pool.bytes;
+    return rc;
+}
 
 int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStream_t st)
 {
@@ -483,6 +673,7 @@ int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStrea
     }
     DASP_TRY(decide_long_variant(h, st, lines));
     if (h->var_long == DASP_VARIANT_BLOCKED && !L.lcb_val) DASP_TRY(build_lcb(h, st));
+    DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
     DASP_CUDA(cudaStreamSynchronize(st));
     h->L.s.device_bytes = h->pool.bytes;
     return DASP_OK;
@@ -543,6 +734,22 @@ int derive(dasp_handle *h, cudaStream_t st)
             DASP_TRY(tmp.alloc((void **)&k1, sizeof(int) * (size_t)ngroups4));
             med_group_keys<<<grid_for(ngroups4, 256), 256, 0, st>>>(L.order_rid, cl, cm, ngroups4, k0, v0);
             DASP_TRY(radix_sort_pairs(tmp, k0, v0, k1, L.med_order, ngroups4, 31, false, st));
+            // When one ascending run already covers most of the groups (a stencil: one dominant length class, rows in
+            // natural order) the identity order IS the local one and the indirection only costs: drop the list.
+            int *desc = nullptr;
+            DASP_TRY(tmp.alloc((void **)&desc, sizeof(int) * 4100));
+            DASP_CUDA(cudaMemsetAsync(desc, 0, sizeof(int) * 4100, st));
+            med_descents<<<grid_for(ngroups4, 256), 256, 0, st>>>(k0, ngroups4, desc);
+            std::vector<int> hd(4100);
+            DASP_CUDA(cudaMemcpyAsync(hd.data(), desc, sizeof(int) * 4100, cudaMemcpyDeviceToHost, st));
+            DASP_CUDA(cudaStreamSynchronize(st));
+            if (hd[0] <= 4096) {
+                std::sort(hd.begin() + 1, hd.begin() + 1 + hd[0]);
+                int longest = 0, prev = 0;
+                for (int i = 1; i <= hd[0]; i++) { longest = std::max(longest, hd[i] - prev); prev = hd[i]; }
+                longest = std::max(longest, ngroups4 - prev);
+                if ((double)longest >= 0.9 * ngroups4) { pool.release(L.med_order); L.med_order = nullptr; }
+            }
         }
         const int f16 = h->dtype == DASP_F16;
         const int G = f16 ? 32 : 8, warps = SPMV_CTA / 32;
@@ -584,6 +791,8 @@ int derive(dasp_handle *h, cudaStream_t st)
 
     // ---- scattered long rows: column-blocked copy ----
     DASP_TRY(decide_long_variant(h, st, lines));
+    // ---- short rows by row band ----
+    DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

@@ -89,6 +89,11 @@ struct SpmvArgs {
     void *lcb_acc;
     unsigned *lcb_done;
     int lcb_bw_log2, lcb_nblk, lcb_nctas, ncols;
+    // short-band kernel (SB, derive.cu): warp items of the four short segments sorted by row band
+    const int *sb_item;     // segment << 28 | warp item inside the segment
+    const int *sb_band_ptr; // [sb_nbands + 1] first item of every band
+    const int *sb_lo;       // [sb_nbands] first column of the band's x window
+    int sb_nbands, sb_wcap;
     int e[7];      // exclusive CTA-range end of category k (long, medium, singles, 1&3, 3/4, 2&2, zero)
     long items[7]; // warp-level work items of category k
 };
@@ -203,6 +208,22 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // x gathers: read-only path, allocate in L1 (neighbouring rows reuse the same entries)
 template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c) { return to_acc(__ldg(x + c)); }
+
+// A window x[lo, lo + len) staged in shared memory (short-band kernel): columns inside it are read from there (a scattered
+// 32-lane gather costs a few bank-conflict cycles instead of 32 L1 wavefronts), the others from global memory.
+template <typename T> struct XWin {
+    const T *xs;
+    int lo;
+    unsigned len;
+};
+template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c, const XWin<T> *w)
+{
+    if (w) {
+        const unsigned d = (unsigned)(c - w->lo);
+        if (d < w->len) return to_acc(w->xs[d]);
+    }
+    return to_acc(__ldg(x + c));
+}
 
 template <typename T>
 __device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Acc<T>::type v)
@@ -737,7 +758,7 @@ __device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, long w)
 // short rows
 
 template <typename T, bool KEEP>
-__device__ __forceinline__ void short_singles(const SpmvArgs &a, long w)
+__device__ __forceinline__ void short_singles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     const T *x = static_cast<const T *>(a.x);
@@ -754,7 +775,7 @@ __device__ __forceinline__ void short_singles(const SpmvArgs &a, long w)
 #pragma unroll
     for (int j = 0; j < SINGLES_PER_THREAD; j++) {
         long i = base + j * 32;
-        if (i < a.n1) store_y<T>(a, a.y1 + i, to_acc(v[j]) * gather(x, c[j]));
+        if (i < a.n1) store_y<T>(a, a.y1 + i, to_acc(v[j]) * gather(x, c[j], win));
     }
 }
 
@@ -771,7 +792,7 @@ template <typename T> __device__ __forceinline__ int paired_y(int tile, int r, i
 // SMMA: the reference's formulation (src/dasp_f64.h:296-483): one DMMA m8n8k4 per 8x4 tile with B masked to the slots
 // that belong to the first / second row of a tile row; the useful results sit on the diagonal of C.
 template <typename T, int MODE, bool KEEP, bool SMMA>
-__device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
+__device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
@@ -828,7 +849,7 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w)
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j]);
+        for (int j = 0; j < SHORT_TILES_PER_WARP; j++) p[j] = to_acc(v[j]) * gather(x, c[j], win);
 #pragma unroll
         for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
             const int tile = tile0 + j;
@@ -862,13 +883,18 @@ __device__ __forceinline__ void zero_rows(const SpmvArgs &a, long w)
     if (i < a.row_zero) store_y<T>(a, a.y0 + i, typename Acc<T>::type(0));
 }
 
+template <typename T> __device__ __forceinline__ void lcb_finalize(const SpmvArgs &a, long w); // below, with the LCB kernel
+
 // MED: 0 one lane per row (large matrices), 1 DMMA tiles, 2 four lanes per row (small matrices)
 // KEEP: the layout fits in L2, streams stay at normal L2 priority (small matrices iterated back to back)
 template <typename T, int MED, int LONGV, bool KEEP, bool SMMA>
 __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w, unsigned char *smem)
 {
     switch (cat) {
-    case 0: long_rows<T, LONGV, KEEP>(a, w, smem); break;
+    case 0:
+        if (a.lcb_nctas > 0) lcb_finalize<T>(a, w); // the column-blocked kernel ran just before on this stream
+        else long_rows<T, LONGV, KEEP>(a, w, smem);
+        break;
     case 1:
         if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, w);
         else medium_rows<T, MED == 1, KEEP>(a, w);
@@ -932,7 +958,6 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T *xs = reinterpret_cast<T *>(dyn_smem);
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int s_last;
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int blo = 0, bhi = a.lcb_nblk; // last block b with cta_first[b] <= c (empty blocks share their successor's value)
     while (bhi - blo > 1) {
@@ -964,22 +989,26 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     const int c0 = __ldg(a.lcb_cta_first + b), nparts = __ldg(a.lcb_cta_first + b + 1) - c0;
     const int psize = (((p1 - p0 + nparts - 1) / nparts) + 1023) & ~1023;
     const int beg = min(p0 + (c - c0) * psize, p1), end = min(beg + psize, p1);
-    const int per = ((end - beg + WARPS * 128 - 1) / (WARPS * 128)) * 128;
-    const int wbeg = beg + warp * per, wend = min(wbeg + per, end);
+    // The part is walked in steps of 128 entries; the warps take chunks of 8 consecutive steps round-robin (step t of the part
+    // belongs to warp (t / 8) % WARPS), so the CTA as a whole streams sequentially and every warp samples the whole part
+    // (slices of very different row-change density would leave most warps waiting for the slowest one).
+    const int nsteps_part = (end - beg + 127) >> 7;
     const T *val = static_cast<const T *>(a.lcb_val);
     const StreamPol pol = make_stream_policy<false>();
     A *acc = static_cast<A *>(a.lcb_acc);
-    if (wbeg < wend) {
+    auto step_addr = [&](int s) { return ((s >> 3) * (8 * WARPS) + warp * 8 + (s & 7)); }; // s-th step of this warp
+    if (step_addr(0) < nsteps_part) {
         T v0[4], v1[4], v2[4];
         int k0[4], k1[4], k2[4];
         bool ok0, ok1, ok2;
-        // a lane past the end of the slice re-reads the indices of the slice's last four entries (rows stay ascending)
+        // a lane past the end of the part re-reads the indices of the part's last four entries (rows stay ascending)
         // and takes zeros as values
-        auto load = [&](T(&v)[4], int(&k)[4], bool &ok, int i) {
-            const int q = i + 4 * lane;
-            ok = q < wend;
-            const int qi = ok ? q : wend - 4;
-            if (i < wend) {
+        auto load = [&](T(&v)[4], int(&k)[4], bool &ok, int s) {
+            const int t = step_addr(s);
+            const int q = beg + 128 * t + 4 * lane;
+            ok = q < end;
+            const int qi = ok ? q : end - 4;
+            if (t < nsteps_part) {
                 ld_stream4<false>(reinterpret_cast<const int *>(a.lcb_idx) + qi, k, pol);
                 if (ok) ld_lcb4(val + q, v, pol);
             }
@@ -991,7 +1020,7 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
             int r[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                r[j] = (int)((unsigned)(ok ? k[j] : k[3]) >> 16); // past the end: the row of the slice's last entry
+                r[j] = (int)((unsigned)(ok ? k[j] : k[3]) >> 16); // past the end: the row of the part's last entry
                 p[j] = ok ? to_acc(v[j]) * to_acc(xs[k[j] & 0xFFFF]) : A(0);
             }
             if (__all_sync(0xffffffffu, r[0] == cur && r[3] == cur)) { lane_acc += (p[0] + p[1]) + (p[2] + p[3]); return; }
@@ -1022,19 +1051,20 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
             cur = new_cur;
         };
         // three steps (3 x 128 entries per warp) in flight: the kernel is bound by DRAM latency x bytes in flight
-        load(v0, k0, ok0, wbeg);
-        load(v1, k1, ok1, wbeg + 128);
+        load(v0, k0, ok0, 0);
+        load(v1, k1, ok1, 1);
         mbar_wait(bar_addr, 0);
         __syncthreads(); // the tail elements written with plain stores
-        for (int i = wbeg; i < wend; i += 384) {
-            load(v2, k2, ok2, i + 256);
+        for (int s = 0;; s += 3) {
+            load(v2, k2, ok2, s + 2);
             consume(v0, k0, ok0);
-            if (i + 128 >= wend) break;
-            load(v0, k0, ok0, i + 384);
+            if (step_addr(s + 1) >= nsteps_part) break;
+            load(v0, k0, ok0, s + 3);
             consume(v1, k1, ok1);
-            if (i + 256 >= wend) break;
-            load(v1, k1, ok1, i + 512);
+            if (step_addr(s + 2) >= nsteps_part) break;
+            load(v1, k1, ok1, s + 4);
             consume(v2, k2, ok2);
+            if (step_addr(s + 3) >= nsteps_part) break;
         }
         if (cur >= 0) {
             const A total = warp_sum(lane_acc);
@@ -1044,19 +1074,89 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
         mbar_wait(bar_addr, 0);
         __syncthreads();
     }
-    // completion: the last CTA of the launch writes y for every long row and re-arms the scratch
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(a.lcb_done, 1u) == (unsigned)(a.lcb_nctas - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int r = tid; r < a.row_long; r += CTA) {
-        const A t = __ldcg(acc + r);
-        store_y<T>(a, r, t);
-        __stcg(acc + r, A(0));
+    // The accumulators become y in the launch that follows on the stream (lcb_finalize below: the long-row slot of the fused
+    // kernel), so this kernel needs neither a grid-wide completion count nor fences.
+}
+
+// y[r] = accumulator of long row r (K11 placement, scatter / axpby forms through store_y), accumulator re-zeroed
+template <typename T> __device__ __forceinline__ void lcb_finalize(const SpmvArgs &a, long w)
+{
+    using A = typename Acc<T>::type;
+    const long r = w * 32 + (threadIdx.x & 31);
+    if (r >= a.row_long) return;
+    A *acc = static_cast<A *>(a.lcb_acc);
+    const A t = __ldcg(acc + r);
+    store_y<T>(a, r, t);
+    __stcg(acc + r, A(0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// short rows by row band (SB): a scattered gather costs the L1 one wavefront per lane (measured: ~0.72 gathers per clock
+// and SM, which caps rows of 1-4 entries far below the HBM roofline).  Here the warp items of the four short segments
+// are sorted by the band of ORIGINAL row ids they start in (derive.cu); a persistent CTA per SM walks bands, stages the
+// band's window of x in shared memory with TMA bulk copies — double buffered: the window of the next band is in flight
+// while this one is multiplied — and runs the same per-segment code as the fused kernel with the gathers served from
+// shared memory (a column outside the window falls back to global memory, so any matrix is handled).
+constexpr int SB_THREADS = 1024;
+constexpr int SB_WARPS = SB_THREADS / 32;
+constexpr int SB_WIN_BYTES = SB_WINDOW_BYTES; // one window buffer: 12288 doubles / 49152 halves
+
+template <typename T>
+__global__ void __launch_bounds__(SB_THREADS, 1) sb_kernel(const __grid_constant__ SpmvArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const T *x = static_cast<const T *>(a.x);
+    const uint32_t bar0 = smem_u32(&bar[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == 0) *a.lcb_done = 0u;
+    __syncthreads();
+    uint64_t keep = 0;
+    if (tid == 0) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep)); // neighbouring bands overlap
+    auto window = [&](int b, int &lo, unsigned &len) { // columns [lo, lo + len): lo is a multiple of 8, len * sizeof(T) of 16
+        lo = __ldg(a.sb_lo + b);
+        const long room = (long)a.ncols - lo;
+        const long n = room < a.sb_wcap ? room : a.sb_wcap;
+        len = n > 0 ? (unsigned)(n & ~(long)(16 / sizeof(T) - 1)) : 0u;
+    };
+    auto issue = [&](int b, int buf) { // thread 0
+        int lo;
+        unsigned len;
+        window(b, lo, len);
+        const uint32_t bytes = len * (uint32_t)sizeof(T), dst = smem_u32(dyn_smem + (size_t)buf * SB_WIN_BYTES);
+        mbar_expect_tx(bar0 + 8 * buf, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+            bulk_g2s(dst + off, reinterpret_cast<const char *>(x + lo) + off, min(32768u, bytes - off), bar0 + 8 * buf, keep);
+    };
+    int b = blockIdx.x;
+    if (b >= a.sb_nbands) return;
+    if (tid == 0) issue(b, 0);
+    for (int it = 0; b < a.sb_nbands; it++, b += gridDim.x) {
+        const int buf = it & 1;
+        if (tid == 0 && b + (int)gridDim.x < a.sb_nbands) issue(b + gridDim.x, buf ^ 1); // that buffer was released by the barrier below
+        XWin<T> win;
+        window(b, win.lo, win.len);
+        win.xs = reinterpret_cast<const T *>(dyn_smem + (size_t)buf * SB_WIN_BYTES);
+        const int i0 = __ldg(a.sb_band_ptr + b), i1 = __ldg(a.sb_band_ptr + b + 1);
+        int e = i0 + warp < i1 ? __ldg(a.sb_item + i0 + warp) : 0; // first item requested before the window arrives
+        mbar_wait(bar0 + 8 * buf, (unsigned)(it >> 1) & 1u); // each buffer's barrier completes one phase per use
+        for (int i = i0 + warp; i < i1; i += SB_WARPS) {
+            const int seg = e >> 28;
+            const long w = e & 0x0FFFFFFF;
+            if (i + SB_WARPS < i1) e = __ldg(a.sb_item + i + SB_WARPS);
+            switch (seg) {
+            case 2: short_singles<T, false>(a, w, &win); break;
+            case 3: short_tiles<T, 0, false, false>(a, w, &win); break;
+            case 4: short_tiles<T, 1, false, false>(a, w, &win); break;
+            default: short_tiles<T, 2, false, false>(a, w, &win); break;
+            }
+        }
+        __syncthreads(); // every warp is done with this window: its buffer may be refilled two bands from now
+    }
 }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -1150,11 +1250,17 @@ static bool lcb_selected(const dasp_handle *h)
            (h->var_long == DASP_VARIANT_BLOCKED || (h->var_long == DASP_VARIANT_AUTO && h->lcb_auto));
 }
 
+static bool sb_selected(const dasp_handle *h)
+{
+    return h->L.sb_nbands > 0 && h->L.sb_nitems > 0 &&
+           (h->var_short == DASP_VARIANT_BANDED || (h->var_short == DASP_VARIANT_AUTO && h->L.sb_auto));
+}
+
 int launches_per_spmv(const dasp_handle *h)
 {
-    if (!lcb_selected(h)) return 1;
-    const dasp_stats_t &s = h->L.s;
-    return (s.m - s.row_long > 0 && (h->category_mask & 14)) ? 2 : 1;
+    // column-blocked long rows and band-staged short rows are launches of their own, followed by the fused kernel (which
+    // also turns the long-row accumulators into y)
+    return 1 + (lcb_selected(h) ? 1 : 0) + (((h->category_mask & 4) && sb_selected(h)) ? 1 : 0);
 }
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
@@ -1286,7 +1392,24 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         else lcb_kernel<double><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
         DASP_CUDA(cudaGetLastError());
     }
-    const int on_long = (cm & 1) && !use_lcb, on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1, on_zero = (cm >> 3) & 1;
+    const int on_long = cm & 1, on_med = (cm >> 1) & 1, on_zero = (cm >> 3) & 1;
+    int on_short = (cm >> 2) & 1;
+    // short rows by row band with x staged in shared memory (its own launch, 2 x 96 KB of shared memory per SM)
+    const bool use_sb = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
+    if (use_sb) {
+        a.sb_item = L.sb_item; a.sb_band_ptr = L.sb_band_ptr; a.sb_lo = L.sb_lo; a.sb_nbands = L.sb_nbands;
+        a.sb_wcap = SB_WIN_BYTES / (f16 ? 2 : 8); a.ncols = L.x_len;
+        if (!h->sb_attr_set) {
+            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SB_WIN_BYTES));
+            h->sb_attr_set = 1;
+        }
+        const int sb_grid = min(L.sb_nbands, h->sm_count > 0 ? h->sm_count : 148);
+        if (f16) sb_kernel<__half><<<sb_grid, SB_THREADS, 2 * SB_WIN_BYTES, st>>>(a);
+        else sb_kernel<double><<<sb_grid, SB_THREADS, 2 * SB_WIN_BYTES, st>>>(a);
+        DASP_CUDA(cudaGetLastError());
+        on_short = 0; // the fused kernel skips the four short segments
+    }
     // medium variant: AUTO = one lane per row.  The 4-lanes-per-row split (the analogue of the reference's
     // rowloop=1 geometry for small matrices, src/dasp_f64.h:533-536) and the DMMA tiles are kept as measured
     // alternatives: both lose on B200 (profiles/r01/variants.md).
@@ -1297,7 +1420,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const bool mma_long = h->var_long == DASP_VARIANT_MMA && !use_lcb;
     const bool tma_long = h->var_long == DASP_VARIANT_TMA && !use_lcb;
     const bool mma_short = !f16 && h->var_short == DASP_VARIANT_MMA;
-    a.items[0] = on_long * (long)L.n_long_units;
+    a.items[0] = on_long * (use_lcb ? (long)cdiv(s.row_long, 32) : (long)L.n_long_units); // LCB: one lane per long row turns its accumulator into y
     a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);
     a.items[2] = on_short * (long)cdiv(s.short_row_1, 32 * SINGLES_PER_THREAD);
     a.items[3] = on_short * (long)cdiv(tiles13, SHORT_TILES_PER_WARP);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 DASP_F64, DASP_F16 = 0, 1
-VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA, VARIANT_BLOCKED = 0, 1, 2, 3, 4, 5
+VARIANT_AUTO, VARIANT_CUDA_CORE, VARIANT_MMA, VARIANT_SPLIT, VARIANT_TMA, VARIANT_BLOCKED, VARIANT_BANDED = 0, 1, 2, 3, 4, 5, 6
 
 _STATS_INT = [
     "dtype", "m", "n", "nnz",  # nnz is int64, handled below
@@ -29,7 +29,7 @@ class _Stats(C.Structure):
                 + [("rate_fill0", C.c_double), ("data_X", C.c_int64), ("data_X2", C.c_int64),
                    ("data_origin1", C.c_int64), ("preprocess_ms", C.c_double), ("device_bytes", C.c_int64),
                    ("col_min", C.c_int), ("col_max", C.c_int), ("long_gather_lines", C.c_double),
-                   ("long_blocked", C.c_int), ("reserved_", C.c_int)])
+                   ("long_blocked", C.c_int), ("short_banded", C.c_int), ("short_band_hit_rate", C.c_double)])
 
 
 def stats_struct_size() -> int:

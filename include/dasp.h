@@ -59,9 +59,13 @@ typedef enum {
                                    only emulated on sm_100a), medium and long rows */
     DASP_VARIANT_SPLIT = 3,     /* medium rows only: CUDA-core, four lanes per row (small, latency-bound matrices) */
     DASP_VARIANT_TMA = 4,       /* long rows only: CUDA-core fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier ring) */
-    DASP_VARIANT_BLOCKED = 5    /* long rows only: column-blocked copy of the long part, x blocks staged in shared memory by
+    DASP_VARIANT_BLOCKED = 5,   /* long rows only: column-blocked copy of the long part, x blocks staged in shared memory by
                                    TMA bulk copies, atomic merge of the split rows; AUTO picks it when the long rows'
                                    gathers are scattered (built on demand otherwise; needs row_long <= 65535) */
+    DASP_VARIANT_BANDED = 6     /* short rows only: the warp items of the four short segments walked by band of original
+                                   rows, the band's window of x staged in shared memory by TMA bulk copies (double
+                                   buffered), gathers served from there; AUTO picks it for large short parts whose entries
+                                   lie inside their band's window (short_band_hit_rate) */
 } dasp_variant;
 
 /* The reference's locals that describe the layout (the 18 structure columns of its CSV record,
@@ -90,7 +94,10 @@ typedef struct dasp_stats_t {
     double long_gather_lines; /* diagnostic: estimated distinct 128-byte lines of x per 32-slot group of the long
                                 part (1 = dense ascending columns, 32 = every gather its own line); above the
                                 crossover AUTO uses the column-blocked long-row kernel (long_blocked != 0) */
-    int long_blocked, reserved_;
+    int long_blocked;         /* AUTO runs the long rows through the column-blocked kernel */
+    int short_banded;         /* AUTO runs the short rows through the band kernel (x windows staged in shared memory) */
+    double short_band_hit_rate; /* diagnostic: fraction of short-row entries whose column lies inside the window of
+                                its row band (0 when the short part is too small for the band kernel) */
 } dasp_stats_t;
 
 /* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,
@@ -164,7 +171,7 @@ int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *o
 int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes,
                 int64_t *bytes);
 
-/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA
+/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA | BANDED
  * (short-row MMA is FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 

@@ -7,7 +7,7 @@
  * It must be included where the reference includes its dasp_f64.h / dasp_f16.h, after (or instead of) the reference's
  * common.h and utils.h, which define MAT_VAL_TYPE / MAT_PTR_TYPE and the helpers the reference's main() uses.
  * Differences, deliberate: a failing call prints the library's error and exits (the reference ignores every CUDA status);
- * nothing is appended to data/*.csv by this function; the 100 + 1000 timing launches are not part of the call
+ * nothing is appended to the data/ CSV records by this function; the 100 + 1000 timing launches are not part of the call
  * (dasp_spmv_timed); FP16 accumulates in fp32.
  */
 #ifndef DASP_REFERENCE_SHIM_H

@@ -66,13 +66,13 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         order = ref["order_rid"]
         tdt = torch.float16 if dtype == oracle.F16 else torch.float64
         dx = torch.from_numpy(x).to(cuda_device)
-        for variant in ([dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED]
-                        if dtype == oracle.F64 else [dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA,
-                                                     dasp.VARIANT_BLOCKED]):  # FP16 MMA = HMMA m16n8k16 (medium and long rows)
-            # medium: cuda/mma/split; long: cuda/mma/tma/blocked; short: cuda/mma (a variant that does not apply = cuda-core)
-            h.set_variant(variant if variant not in (dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED) else dasp.VARIANT_CUDA_CORE,
-                          variant if variant != dasp.VARIANT_SPLIT else dasp.VARIANT_CUDA_CORE,
-                          variant if variant == dasp.VARIANT_MMA else dasp.VARIANT_AUTO)
+        C_, M_, S_, T_, B_, N_ = (dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED,
+                                  dasp.VARIANT_BANDED)
+        # (medium, long, short): medium cuda/mma/split; long cuda/mma/tma/blocked; short cuda/mma(FP64 only)/banded.
+        # FP16 MMA = HMMA m16n8k16 (medium and long rows); the last triple is also used for the original-order product below
+        triples = [(C_, C_, C_), (M_, M_, M_ if dtype == oracle.F64 else C_), (S_, C_, C_), (C_, T_, C_), (C_, C_, N_), (C_, B_, N_)]
+        for variant in triples:
+            h.set_variant(*variant)
             for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
                 dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
                 h.spmv(dx, dy, torch.cuda.current_stream().cuda_stream)
@@ -85,14 +85,14 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
                     assert np.max(np.abs(y.astype(np.float64) - y_ref[order]), initial=0.0) <= FP16_ABS_TOL
                     assert _rel_l2(y, y_ref[order]) <= FP16_REL_TOL, f"{name}"
             # the same product with the kernels reading reg_cid instead of the compact 16-bit indices: bit-equal
-            if variant == dasp.VARIANT_CUDA_CORE:
+            if variant == (C_, C_, C_):
                 h.set_index_compression(False)
                 dy2 = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
                 h.spmv(dx, dy2, torch.cuda.current_stream().cuda_stream)
                 torch.cuda.synchronize()
                 h.set_index_compression(True)
                 assert bool(torch.equal(dy2, dy)), f"{name}: compact indices change the result"
-            # original-order output (the last variant of the loop is still selected: the blocked long rows)
+            # original-order output (the last variant of the loop is still selected: blocked long rows, banded short rows)
             dy = torch.full((max(m, 1),), float("nan"), dtype=tdt, device=cuda_device)
             h.spmv_unpermuted(dx, dy, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()

@@ -21,25 +21,21 @@ def test_dasp_h_is_c99():
                " return dasp_spmv(h, x, y, 0) + (int)sizeof(dasp_synth_spec); }\n")
 
 
-def test_reference_shim_of_integration_md_compiles():
-    """The spmv_all shim shown in INTEGRATION.md, compiled as C against include/dasp.h for both precisions."""
-    shim = '''
-#include "dasp.h"
-#include <stdio.h>
-#include <stdlib.h>
-#define MAT_PTR_TYPE int
-static void spmv_all(char *filename, MAT_VAL_TYPE *csrValA, MAT_PTR_TYPE *csrRowPtrA, int *csrColIdxA,
-                     MAT_VAL_TYPE *X_val, MAT_VAL_TYPE *Y_val, int *order_rid,
-                     int rowA, int colA, MAT_PTR_TYPE nnzA, int NUM, double threshold, int block_longest)
-{
-    int rc = SPMV_ALL(filename, csrValA, csrRowPtrA, csrColIdxA, X_val, Y_val, order_rid,
-                      rowA, colA, nnzA, NUM, threshold, block_longest);
-    if (rc != DASP_OK) { fprintf(stderr, "dasp: %s: %s\\n", dasp_strerror(rc), dasp_last_error()); exit(1); }
-}
-int main(void) { (void)spmv_all; return 0; }
-'''
-    _compile_c("#define MAT_VAL_TYPE double\n#define SPMV_ALL dasp_spmv_all_f64\n" + shim)
-    _compile_c("#define MAT_VAL_TYPE unsigned short\n#define SPMV_ALL dasp_spmv_all_f16\n" + shim)
+def test_reference_shim_header_compiles_for_both_precisions():
+    """include/dasp_reference_shim.h (the reference-side binding INTEGRATION.md describes): the reference's spmv_all argument
+    list on the C ABI, compiled as plain C with the two macro settings of the reference's common.h (-D f64 / half)."""
+    body = ('#define MAT_PTR_TYPE int\n#include "dasp_reference_shim.h"\n'
+            "int main(void) { char name[] = \"m\"; MAT_VAL_TYPE v[1]; int rp[2] = {0, 0}, ci[1], o[1];\n"
+            "  spmv_all(name, v, rp, ci, v, v, o, 0, 0, 0, 4, 0.75, 256); return 0; }\n")
+    _compile_c("#define f64\n#define MAT_VAL_TYPE double\n" + body)
+    _compile_c("#define MAT_VAL_TYPE unsigned short\n" + body)
+
+
+def test_shim_requires_the_reference_types():
+    import pytest
+
+    with pytest.raises(subprocess.CalledProcessError):
+        _compile_c('#include "dasp_reference_shim.h"\nint main(void) { return 0; }\n')
 
 
 def test_oracle_header_is_c99():
