@@ -174,8 +174,8 @@ constexpr int SHORT_TILES_PER_WARP = 4; // 8x4 tiles of a short segment per warp
 constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
 constexpr int LCB_PART = 32768;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
-constexpr int SB_BAND_ROWS = 4096;  // original rows per band of the short-band kernel
-constexpr int SB_WINDOW_BYTES = 98304; // bytes of x one band stages in shared memory (must match spmv.cu SB_WIN_BYTES)
+constexpr int SB_BAND_ROWS = 16384; // original rows per band of the short-band kernel
+constexpr int SB_WINDOW_BYTES = 196608; // bytes of x one band stages in shared memory: 24576 doubles = the band + 4096 columns either side
 
 // preprocess.cu
 int scan_inplace(DevicePool &tmp_pool, int *d, int count, cudaStream_t st);

@@ -551,8 +551,10 @@ template <typename T> int build_short_bands_t(dasp_handle *h, cudaStream_t st, b
     DASP_CUDA(cudaGetLastError());
     L.sb_nbands = g.nbands; L.sb_nitems = nitems;
     L.sb_hit_rate = hc[1] ? (double)hc[0] / (double)hc[1] : 0.0;
-    // worth it when nearly every gather is served from the window (measured crossover: profiles/r02/README.md)
-    L.sb_auto = nitems > 0 && L.sb_hit_rate >= 0.8;
+    // worth it when nearly every gather is served from the window AND every SM gets enough bands for the persistent CTAs to
+    // balance (measured, profiles/r02/README.md: +5 % on the 3052 bands of C5, -15 % on the 611 bands of C3)
+    const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    L.sb_auto = nitems > 0 && L.sb_hit_rate >= 0.8 && g.nbands >= 16 * sms;
     L.s.short_band_hit_rate = L.sb_hit_rate;
     L.s.short_banded = L.sb_auto;
     return DASP_OK;
@@ -597,7 +599,7 @@ int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long lon
         DASP_CUDA(cudaStreamSynchronize(st));
         L.long_lines_avg = (double)nl / ((double)s.fill0_nnz_long / 32.0);
         L.s.long_gather_lines = L.long_lines_avg;
-        double thr = 20.0; // measured crossover (profiles/r02/README.md): 12.5 lines -> chunked wins, 31.7 -> column-blocked wins
+        double thr = 9.0; // measured crossover (profiles/r02/README.md): 5.1 lines (C5 sorted) -> chunked wins 1.69 vs 1.83 ms; 12.5 (C3 sorted) -> column-blocked wins 0.339 vs 0.372 ms; 31.7 / 32 (spec generators) -> column-blocked wins by 1.9x / 8x
         if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
         if (L.long_lines_avg > thr && s.row_long <= 65535 && s.nnz_long >= 4 * LCB_PART) {
             DASP_TRY(build_lcb(h, st));

@@ -757,8 +757,49 @@ __device__ __forceinline__ void medium_rows_split(const SpmvArgs &a, long w)
 // ------------------------------------------------------------------------------------------------
 // short rows
 
+// values and column indices of one warp item of a short segment (4 slots per lane in every segment), so that a kernel
+// can request the streams of its next item before it multiplies the current one (short-band kernel)
+template <typename T> struct ShortRegs {
+    T v[4];
+    int c[4];
+};
+static_assert(SINGLES_PER_THREAD == 4 && SHORT_TILES_PER_WARP == 4, "ShortRegs holds 4 slots per lane");
+
+template <typename T>
+__device__ __forceinline__ void short_load(const SpmvArgs &a, int seg, long w, ShortRegs<T> &R, const StreamPol &pol)
+{
+    const int lane = threadIdx.x & 31;
+    if (seg == 2) { // singles
+        const T *val = static_cast<const T *>(a.short_val) + a.s1;
+        const int *cid = a.short_cid + a.s1;
+        const long base = w * 32 * SINGLES_PER_THREAD + lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long i = base + j * 32;
+            const bool ok = i < a.n1;
+            R.v[j] = ok ? ld_stream1(val + i, pol) : T(0);
+            R.c[j] = ok ? ld_stream1(cid + i, pol) : 0;
+        }
+        return;
+    }
+    constexpr int G = sizeof(T) == 8 ? 8 : 32;
+    const int sbase = seg == 3 ? a.s13 : (seg == 4 ? a.s34 : a.s22);
+    const int nrows = seg == 3 ? a.c13 : (seg == 4 ? a.n34 : a.n2);
+    const T *val = static_cast<const T *>(a.short_val) + sbase;
+    const int *cid = a.short_cid + sbase;
+    const int tile0 = (int)w * SHORT_TILES_PER_WARP;
+    const int tiles_avail = seg == 5 ? (int)(((long)nrows + 2 * G - 1) / (2 * G)) * (G >> 3) : (nrows + 7) / 8;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool ok = tile0 + j < tiles_avail;
+        const long s = (long)(tile0 + j) * 32 + lane;
+        R.v[j] = ok ? ld_stream1(val + s, pol) : T(0);
+        R.c[j] = ok ? ld_stream1(cid + s, pol) : 0;
+    }
+}
+
 template <typename T, bool KEEP>
-__device__ __forceinline__ void short_singles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
+__device__ __forceinline__ void short_singles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr, const ShortRegs<T> *pre = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     const T *x = static_cast<const T *>(a.x);
@@ -770,7 +811,8 @@ __device__ __forceinline__ void short_singles(const SpmvArgs &a, long w, const X
 #pragma unroll
     for (int j = 0; j < SINGLES_PER_THREAD; j++) {
         long i = base + j * 32;
-        if (i < a.n1) { v[j] = ld_stream1(val + i, pol); c[j] = ld_stream1(cid + i, pol); }
+        if (pre) { v[j] = pre->v[j]; c[j] = pre->c[j]; }
+        else if (i < a.n1) { v[j] = ld_stream1(val + i, pol); c[j] = ld_stream1(cid + i, pol); }
     }
 #pragma unroll
     for (int j = 0; j < SINGLES_PER_THREAD; j++) {
@@ -792,7 +834,7 @@ template <typename T> __device__ __forceinline__ int paired_y(int tile, int r, i
 // SMMA: the reference's formulation (src/dasp_f64.h:296-483): one DMMA m8n8k4 per 8x4 tile with B masked to the slots
 // that belong to the first / second row of a tile row; the useful results sit on the diagonal of C.
 template <typename T, int MODE, bool KEEP, bool SMMA>
-__device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
+__device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w, const XWin<T> *win = nullptr, const ShortRegs<T> *pre = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
@@ -813,8 +855,8 @@ __device__ __forceinline__ void short_tiles(const SpmvArgs &a, long w, const XWi
     for (int j = 0; j < SHORT_TILES_PER_WARP; j++) {
         bool ok = tile0 + j < tiles_avail;
         long s = (long)(tile0 + j) * 32 + lane;
-        v[j] = ok ? ld_stream1(val + s, pol) : T(0);
-        c[j] = ok ? ld_stream1(cid + s, pol) : 0;
+        if (pre) { v[j] = pre->v[j]; c[j] = pre->c[j]; }
+        else { v[j] = ok ? ld_stream1(val + s, pol) : T(0); c[j] = ok ? ld_stream1(cid + s, pol) : 0; }
     }
     const int r = lane >> 2, q = lane & 3;
     if constexpr (SMMA && sizeof(T) == 8) {
@@ -1094,68 +1136,76 @@ template <typename T> __device__ __forceinline__ void lcb_finalize(const SpmvArg
 // short rows by row band (SB): a scattered gather costs the L1 one wavefront per lane (measured: ~0.72 gathers per clock
 // and SM, which caps rows of 1-4 entries far below the HBM roofline).  Here the warp items of the four short segments
 // are sorted by the band of ORIGINAL row ids they start in (derive.cu); a persistent CTA per SM walks bands, stages the
-// band's window of x in shared memory with TMA bulk copies — double buffered: the window of the next band is in flight
-// while this one is multiplied — and runs the same per-segment code as the fused kernel with the gathers served from
-// shared memory (a column outside the window falls back to global memory, so any matrix is handled).
+// band's window of x (192 KB: the band's 16384 columns plus 4096 either side) in shared memory with TMA bulk copies and
+// runs the same per-segment code as the fused kernel with the gathers served from shared memory (a column outside the
+// window falls back to global memory, so any matrix is handled).
 constexpr int SB_THREADS = 1024;
 constexpr int SB_WARPS = SB_THREADS / 32;
-constexpr int SB_WIN_BYTES = SB_WINDOW_BYTES; // one window buffer: 12288 doubles / 49152 halves
+constexpr int SB_WIN_BYTES = SB_WINDOW_BYTES;
 
 template <typename T>
 __global__ void __launch_bounds__(SB_THREADS, 1) sb_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x, warp = tid >> 5;
     const T *x = static_cast<const T *>(a.x);
-    const uint32_t bar0 = smem_u32(&bar[0]);
+    const StreamPol pol = make_stream_policy<false>();
+    const uint32_t bar0 = smem_u32(&bar);
     if (tid == 0) {
         mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     uint64_t keep = 0;
     if (tid == 0) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep)); // neighbouring bands overlap
-    auto window = [&](int b, int &lo, unsigned &len) { // columns [lo, lo + len): lo is a multiple of 8, len * sizeof(T) of 16
-        lo = __ldg(a.sb_lo + b);
-        const long room = (long)a.ncols - lo;
-        const long n = room < a.sb_wcap ? room : a.sb_wcap;
-        len = n > 0 ? (unsigned)(n & ~(long)(16 / sizeof(T) - 1)) : 0u;
-    };
-    auto issue = [&](int b, int buf) { // thread 0
-        int lo;
-        unsigned len;
-        window(b, lo, len);
-        const uint32_t bytes = len * (uint32_t)sizeof(T), dst = smem_u32(dyn_smem + (size_t)buf * SB_WIN_BYTES);
-        mbar_expect_tx(bar0 + 8 * buf, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768u)
-            bulk_g2s(dst + off, reinterpret_cast<const char *>(x + lo) + off, min(32768u, bytes - off), bar0 + 8 * buf, keep);
-    };
-    int b = blockIdx.x;
-    if (b >= a.sb_nbands) return;
-    if (tid == 0) issue(b, 0);
-    for (int it = 0; b < a.sb_nbands; it++, b += gridDim.x) {
-        const int buf = it & 1;
-        if (tid == 0 && b + (int)gridDim.x < a.sb_nbands) issue(b + gridDim.x, buf ^ 1); // that buffer was released by the barrier below
+    int it = 0;
+    for (int b = blockIdx.x; b < a.sb_nbands; b += gridDim.x, it++) {
+        // window of this band: columns [lo, lo + len), lo a multiple of 8, len * sizeof(T) a multiple of 16
         XWin<T> win;
-        window(b, win.lo, win.len);
-        win.xs = reinterpret_cast<const T *>(dyn_smem + (size_t)buf * SB_WIN_BYTES);
-        const int i0 = __ldg(a.sb_band_ptr + b), i1 = __ldg(a.sb_band_ptr + b + 1);
-        int e = i0 + warp < i1 ? __ldg(a.sb_item + i0 + warp) : 0; // first item requested before the window arrives
-        mbar_wait(bar0 + 8 * buf, (unsigned)(it >> 1) & 1u); // each buffer's barrier completes one phase per use
-        for (int i = i0 + warp; i < i1; i += SB_WARPS) {
-            const int seg = e >> 28;
-            const long w = e & 0x0FFFFFFF;
-            if (i + SB_WARPS < i1) e = __ldg(a.sb_item + i + SB_WARPS);
-            switch (seg) {
-            case 2: short_singles<T, false>(a, w, &win); break;
-            case 3: short_tiles<T, 0, false, false>(a, w, &win); break;
-            case 4: short_tiles<T, 1, false, false>(a, w, &win); break;
-            default: short_tiles<T, 2, false, false>(a, w, &win); break;
-            }
+        win.lo = __ldg(a.sb_lo + b);
+        const long room = (long)a.ncols - win.lo;
+        const long n = room < a.sb_wcap ? room : a.sb_wcap;
+        win.len = n > 0 ? (unsigned)(n & ~(long)(16 / sizeof(T) - 1)) : 0u;
+        win.xs = reinterpret_cast<const T *>(dyn_smem);
+        if (tid == 0) {
+            const uint32_t bytes = win.len * (uint32_t)sizeof(T), dst = smem_u32(dyn_smem);
+            mbar_expect_tx(bar0, bytes);
+            for (uint32_t off = 0; off < bytes; off += 32768u)
+                bulk_g2s(dst + off, reinterpret_cast<const char *>(x + win.lo) + off, min(32768u, bytes - off), bar0, keep);
         }
-        __syncthreads(); // every warp is done with this window: its buffer may be refilled two bands from now
+        const int i0 = __ldg(a.sb_band_ptr + b), i1 = __ldg(a.sb_band_ptr + b + 1);
+        // Software pipeline over the warp's items: the value / index streams of item k+1 (and the id of item k+2) are
+        // requested before item k is multiplied, so loads are in flight all the time; the first item's streams are
+        // requested while the window itself is still arriving.
+        auto multiply = [&](int e, const ShortRegs<T> &R) {
+            const long w = e & 0x0FFFFFFF;
+            switch (e >> 28) {
+            case 2: short_singles<T, false>(a, w, &win, &R); break;
+            case 3: short_tiles<T, 0, false, false>(a, w, &win, &R); break;
+            case 4: short_tiles<T, 1, false, false>(a, w, &win, &R); break;
+            default: short_tiles<T, 2, false, false>(a, w, &win, &R); break;
+            }
+        };
+        ShortRegs<T> R0, R1;
+        int i = i0 + warp;
+        int e0 = i < i1 ? __ldg(a.sb_item + i) : 0, e1 = i + SB_WARPS < i1 ? __ldg(a.sb_item + i + SB_WARPS) : 0;
+        if (i < i1) short_load<T>(a, e0 >> 28, e0 & 0x0FFFFFFF, R0, pol);
+        mbar_wait(bar0, (unsigned)it & 1u);
+        for (; i < i1; i += 2 * SB_WARPS) {
+            const bool has1 = i + SB_WARPS < i1;
+            if (has1) short_load<T>(a, e1 >> 28, e1 & 0x0FFFFFFF, R1, pol);
+            const int e2 = i + 2 * SB_WARPS < i1 ? __ldg(a.sb_item + i + 2 * SB_WARPS) : 0;
+            multiply(e0, R0);
+            if (!has1) break;
+            const bool has2 = i + 2 * SB_WARPS < i1;
+            if (has2) short_load<T>(a, e2 >> 28, e2 & 0x0FFFFFFF, R0, pol);
+            const int e3 = i + 3 * SB_WARPS < i1 ? __ldg(a.sb_item + i + 3 * SB_WARPS) : 0;
+            multiply(e1, R1);
+            e0 = e2;
+            e1 = e3;
+        }
+        __syncthreads(); // every warp is done with the window before the next band overwrites it
     }
 }
 
@@ -1394,19 +1444,19 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     }
     const int on_long = cm & 1, on_med = (cm >> 1) & 1, on_zero = (cm >> 3) & 1;
     int on_short = (cm >> 2) & 1;
-    // short rows by row band with x staged in shared memory (its own launch, 2 x 96 KB of shared memory per SM)
+    // short rows by row band with x staged in shared memory (its own launch, 192 KB of shared memory per SM)
     const bool use_sb = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
     if (use_sb) {
         a.sb_item = L.sb_item; a.sb_band_ptr = L.sb_band_ptr; a.sb_lo = L.sb_lo; a.sb_nbands = L.sb_nbands;
         a.sb_wcap = SB_WIN_BYTES / (f16 ? 2 : 8); a.ncols = L.x_len;
         if (!h->sb_attr_set) {
-            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SB_WIN_BYTES));
-            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(sb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_WIN_BYTES));
             h->sb_attr_set = 1;
         }
         const int sb_grid = min(L.sb_nbands, h->sm_count > 0 ? h->sm_count : 148);
-        if (f16) sb_kernel<__half><<<sb_grid, SB_THREADS, 2 * SB_WIN_BYTES, st>>>(a);
-        else sb_kernel<double><<<sb_grid, SB_THREADS, 2 * SB_WIN_BYTES, st>>>(a);
+        if (f16) sb_kernel<__half><<<sb_grid, SB_THREADS, SB_WIN_BYTES, st>>>(a);
+        else sb_kernel<double><<<sb_grid, SB_THREADS, SB_WIN_BYTES, st>>>(a);
         DASP_CUDA(cudaGetLastError());
         on_short = 0; // the fused kernel skips the four short segments
     }
