@@ -58,6 +58,7 @@ def parse():
                          "into equal chunks + all-gather, measured slower: 3.18 vs 2.34 ms per step on 8 GPUs; p2p / mc: fused, the "
                          "SpMV kernel stores y straight into every peer's next x through NVLink peer mappings / one NVSwitch "
                          "multicast mapping, the all-reduce of the norm is the only collective)")
+    ap.add_argument("--slab", default="", metavar="R/W", help="diagnostic: run rank R's slab of a W-way partition on one GPU, no process group")
     ap.add_argument("--no-iterated", action="store_true", help="skip the C5 100-step power-iteration leg (`iterated` key)")
     ap.add_argument("--power-iter", type=int, default=0, metavar="K",
                     help="iterated workload: K steps of x <- A x / ||A x|| with the y slabs gathered over NCCL every step")
@@ -292,6 +293,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    fake = None
+    if args.slab:
+        fake = tuple(int(t) for t in args.slab.split("/"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     dev = torch.device(f"cuda:{local}")
@@ -313,11 +317,12 @@ def run_ours(args):
     ln = synth.row_lengths(spec, 0, m, dev)
     cs = torch.cumsum(ln, 0)  # cs[i] = rowptr[i+1]
     nnz_total = int(cs[-1].item())
-    targets = torch.tensor([nnz_total * p // world for p in range(1, world)], device=dev, dtype=torch.int64)
+    parts = fake[1] if fake else world
+    targets = torch.tensor([nnz_total * p // parts for p in range(1, parts)], device=dev, dtype=torch.int64)
     cuts = [0] + [int(c) + 1 for c in torch.searchsorted(cs, targets, right=False).tolist()] + [m]
     cuts = [min(c, m) for c in cuts]
     del ln, cs
-    r0, r1 = cuts[rank], cuts[rank + 1]
+    r0, r1 = (cuts[fake[0]], cuts[fake[0] + 1]) if fake else (cuts[rank], cuts[rank + 1])
 
     rp, ci, v, nnz = synth.generate(spec, r0, r1, dev, half=half)
     t0 = time.perf_counter()

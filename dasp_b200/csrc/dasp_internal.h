@@ -135,7 +135,7 @@ struct Layout {
     unsigned *lcb_idx = nullptr;            // [lcb_live] long-row index << 16 | column - block * width (row_long <= 65535)
     int *lcb_blk_ptr = nullptr;             // [lcb_nblk + 1] first entry of each block (multiples of 4)
     int *lcb_cta_first = nullptr;           // [lcb_nblk + 1] first CTA of each block
-    void *lcb_acc = nullptr;                // [row_long] accumulators (double / float), zero between launches
+    void *lcb_acc = nullptr;                // [LCB_COPIES][lcb_acc_stride] accumulators (double / float), zero between launches
     unsigned *lcb_done = nullptr;           // [1] CTAs finished in the current launch (self-resetting)
 };
 
@@ -172,7 +172,15 @@ constexpr int SPMV_CTA = 256;           // threads per CTA of the fused kernel (
 constexpr int SINGLES_PER_THREAD = 4;   // single-entry rows per thread
 constexpr int SHORT_TILES_PER_WARP = 4; // 8x4 tiles of a short segment per warp
 constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
-constexpr int LCB_PART = 32768;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
+#ifndef DASP_LCB_PART
+#define DASP_LCB_PART 32768
+#endif
+#ifndef DASP_LCB_COPIES
+#define DASP_LCB_COPIES 8
+#endif
+constexpr int LCB_PART = DASP_LCB_PART;     // most entries one CTA of the column-blocked long-row kernel takes; a block is cut into equal parts
+constexpr int LCB_COPIES = DASP_LCB_COPIES;       // private copies of the long-row accumulators (CTA c adds into copy c % 8): with one copy
+                                    // every atomic of the GPU lands on row_long * 8 bytes, a handful of L2 lines
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
 constexpr int SB_BAND_ROWS = 16384; // original rows per band of the short-band kernel
 constexpr int SB_WINDOW_BYTES = 196608; // bytes of x one band stages in shared memory: 24576 doubles = the band + 4096 columns either side

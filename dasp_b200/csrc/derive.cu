@@ -211,32 +211,40 @@ __global__ void sb_item_keys(const int *__restrict__ order_rid, SbGeom g, int to
 // smallest column of every band (padding slots, value 0 and column 0, ignored): one warp per item
 template <typename T>
 __global__ void sb_min_col(const int *__restrict__ sorted_item, const int *__restrict__ sorted_band, int nitems, SbGeom g,
-                           const T *__restrict__ short_val, const int *__restrict__ short_cid, int *__restrict__ lo)
+                           const T *__restrict__ short_val, const int *__restrict__ short_cid, int *__restrict__ lo,
+                           int *__restrict__ hi)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= nitems) return;
     const int e = sorted_item[i], c = (e >> 28) - 2, local = e & 0x0FFFFFFF;
     const long s0 = (long)local * g.slots[c];
-    int mn = INT32_MAX;
+    int mn = INT32_MAX, mx = -1;
     for (int k = lane; k < g.slots[c]; k += 32) {
         const long p = s0 + k;
         if (p < g.nslots[c]) {
             const int col = short_cid[g.sbase[c] + p];
-            if (!(col == 0 && short_val[g.sbase[c] + p] == T(0))) mn = min(mn, col);
+            // (the single of a 1&3 pair, slot 0 of its tile row, belongs to a row from elsewhere: it does not place the window)
+            if (!(col == 0 && short_val[g.sbase[c] + p] == T(0)) && !(c == 1 && (p & 3) == 0)) { mn = min(mn, col); mx = max(mx, col); }
         }
     }
-    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    if (lane == 0 && mn != INT32_MAX) atomicMin(lo + sorted_band[i], mn);
+    for (int o = 16; o; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0 && mx >= 0) { atomicMin(lo + sorted_band[i], mn); atomicMax(hi + sorted_band[i], mx); }
 }
-// window start of every band: the smallest column, but not left of (diagonal position of the band - half a window), so that
-// a few outlying columns cannot drag the window away from where the band's entries are; multiple of 8
-__global__ void sb_place_windows(int *__restrict__ lo, int nbands, int band_rows, int m, int n, int wcap)
+// window start of every band: the smallest column when all columns of the band fit one window (any banded structure,
+// row slabs included); otherwise the smallest column but not left of (diagonal position of the band - half a window), so
+// that a few outlying columns cannot drag the window away from where a square matrix keeps the band's entries; multiple of 8
+__global__ void sb_place_windows(int *__restrict__ lo, const int *__restrict__ hi, int nbands, int band_rows, int m, int n, int wcap)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbands) return;
-    const long centre = (long)(((double)b * band_rows + band_rows / 2) * (double)n / (double)(m > 0 ? m : 1));
     long v = lo[b] == INT32_MAX ? 0 : lo[b];
-    v = max(v, centre - wcap / 2);
+    if ((long)hi[b] - v >= wcap) {
+        const long centre = (long)(((double)b * band_rows + band_rows / 2) * (double)n / (double)(m > 0 ? m : 1));
+        v = max(v, centre - wcap / 2);
+    }
     v = min(v, (long)max(0, n - 1));
     lo[b] = (int)(v & ~7L);
 }
@@ -303,13 +311,14 @@ __global__ void lcb_block_ptr(const int *__restrict__ sorted_key, int slots, int
 }
 
 // padded entry count of every block: a multiple of 4 (one 256-bit value load + one 128-bit index load per lane)
-__global__ void lcb_padded_counts(const int *__restrict__ blk_ptr, int nblk, int *__restrict__ pad_ptr, int *__restrict__ cta_first)
+__global__ void lcb_padded_counts(const int *__restrict__ blk_ptr, int nblk, int part, int *__restrict__ pad_ptr,
+                                  int *__restrict__ cta_first)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nblk) return;
     const int cnt = b < nblk ? ((blk_ptr[b + 1] - blk_ptr[b] + 3) & ~3) : 0;
     pad_ptr[b] = cnt;
-    cta_first[b] = (cnt + LCB_PART - 1) / LCB_PART;
+    cta_first[b] = (cnt + part - 1) / part;
 }
 
 // entry i of the padded, blocked sequence: value, and (long row << 16 | column inside the block); pad entries repeat the
@@ -361,7 +370,10 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     DASP_TRY(pool.alloc((void **)&L.lcb_blk_ptr, sizeof(int) * (size_t)(nblk + 1)));
     DASP_TRY(pool.alloc((void **)&L.lcb_cta_first, sizeof(int) * (size_t)(nblk + 1)));
     lcb_block_ptr<<<grid_for(nblk + 1, 256), 256, 0, st>>>(skey, slots, nblk, blk_ptr);
-    lcb_padded_counts<<<grid_for(nblk + 1, 256), 256, 0, st>>>(blk_ptr, nblk, L.lcb_blk_ptr, L.lcb_cta_first);
+    // entries per CTA: a bigger part amortises the 64 KB block of x a CTA stages, a smaller one gives a small matrix enough
+    // CTAs to balance (measured, profiles/r02: C5 1e9 entries 2.10 -> 1.99 ms with 65536, C3 1.4e8 entries 0.339 -> 0.354 ms)
+    const int part = (long)s.nnz_long >= 16L * 444 * 65536 ? 65536 : LCB_PART;
+    lcb_padded_counts<<<grid_for(nblk + 1, 256), 256, 0, st>>>(blk_ptr, nblk, part, L.lcb_blk_ptr, L.lcb_cta_first);
     DASP_TRY(scan_inplace(tmp, L.lcb_blk_ptr, nblk + 1, st));
     DASP_TRY(scan_inplace(tmp, L.lcb_cta_first, nblk + 1, st));
     int tot[2] = {0, 0};
@@ -372,9 +384,10 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     if (total < 0) { set_error("column-blocked long part exceeds 32-bit offsets"); return DASP_ERR_RANGE; }
     DASP_TRY(pool.alloc(&L.lcb_val, sizeof(T) * (size_t)total));
     DASP_TRY(pool.alloc((void **)&L.lcb_idx, sizeof(unsigned) * (size_t)total));
-    DASP_TRY(pool.alloc(&L.lcb_acc, 8 * (size_t)s.row_long));
+    const size_t acc_stride = ((size_t)s.row_long + 31) & ~(size_t)31; // copies start on their own 256-byte boundary
     DASP_TRY(pool.alloc((void **)&L.lcb_done, sizeof(unsigned) * 4));
-    DASP_CUDA(cudaMemsetAsync(L.lcb_acc, 0, 8 * (size_t)s.row_long, st));
+    DASP_TRY(pool.alloc(&L.lcb_acc, 8 * acc_stride * LCB_COPIES));
+    DASP_CUDA(cudaMemsetAsync(L.lcb_acc, 0, 8 * acc_stride * LCB_COPIES, st));
     DASP_CUDA(cudaMemsetAsync(L.lcb_done, 0, sizeof(unsigned) * 4, st));
     if (total > 0)
         lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.k_long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
@@ -541,9 +554,12 @@ template <typename T> int build_short_bands_t(dasp_handle *h, cudaStream_t st, b
     DASP_TRY(tmp.alloc((void **)&counts, sizeof(unsigned long long) * 2));
     DASP_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 2, st));
     if (nitems > 0) {
-        sb_min_col<T><<<grid_for((long)nitems * 32, 256), 256, 0, st>>>(L.sb_item, k1, nitems, g, sval, L.k_short_cid, L.sb_lo);
+        int *hi = nullptr;
+        DASP_TRY(tmp.alloc((void **)&hi, sizeof(int) * (size_t)(g.nbands + 1)));
+        DASP_CUDA(cudaMemsetAsync(hi, 0xff, sizeof(int) * (size_t)(g.nbands + 1), st)); // -1
+        sb_min_col<T><<<grid_for((long)nitems * 32, 256), 256, 0, st>>>(L.sb_item, k1, nitems, g, sval, L.k_short_cid, L.sb_lo, hi);
         sb_fix_unset<<<grid_for(g.nbands + 1, 256), 256, 0, st>>>(L.sb_lo, g.nbands + 1);
-        sb_place_windows<<<grid_for(g.nbands, 256), 256, 0, st>>>(L.sb_lo, g.nbands, SB_BAND_ROWS, s.m, L.x_len, wcap);
+        sb_place_windows<<<grid_for(g.nbands, 256), 256, 0, st>>>(L.sb_lo, hi, g.nbands, SB_BAND_ROWS, s.m, L.x_len, wcap);
         sb_hits<T><<<grid_for((long)nitems * 32, 256), 256, 0, st>>>(L.sb_item, k1, nitems, g, sval, L.k_short_cid, L.sb_lo, wcap, counts);
     }
     DASP_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));

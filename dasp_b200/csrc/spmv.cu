@@ -1037,7 +1037,8 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     const int nsteps_part = (end - beg + 127) >> 7;
     const T *val = static_cast<const T *>(a.lcb_val);
     const StreamPol pol = make_stream_policy<false>();
-    A *acc = static_cast<A *>(a.lcb_acc);
+    const int acc_stride = (a.row_long + 31) & ~31;
+    A *acc = static_cast<A *>(a.lcb_acc) + (size_t)(c & (LCB_COPIES - 1)) * acc_stride; // this CTA's private copy
     auto step_addr = [&](int s) { return ((s >> 3) * (8 * WARPS) + warp * 8 + (s & 7)); }; // s-th step of this warp
     if (step_addr(0) < nsteps_part) {
         T v0[4], v1[4], v2[4];
@@ -1127,9 +1128,14 @@ template <typename T> __device__ __forceinline__ void lcb_finalize(const SpmvArg
     const long r = w * 32 + (threadIdx.x & 31);
     if (r >= a.row_long) return;
     A *acc = static_cast<A *>(a.lcb_acc);
-    const A t = __ldcg(acc + r);
+    const int acc_stride = (a.row_long + 31) & ~31;
+    A t = 0;
+#pragma unroll
+    for (int k = 0; k < LCB_COPIES; k++) { // the private copies of the CTAs, in a fixed order
+        t += __ldcg(acc + (size_t)k * acc_stride + r);
+        __stcg(acc + (size_t)k * acc_stride + r, A(0));
+    }
     store_y<T>(a, r, t);
-    __stcg(acc + r, A(0));
 }
 
 // ------------------------------------------------------------------------------------------------

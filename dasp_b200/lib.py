@@ -45,7 +45,8 @@ class DaspError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libdasp_b200.so")
+    # DASP_B200_LIB: A/B aid of the tuning sweeps (an alternative build of the same sources); never set in tests or the bench
+    return os.environ.get("DASP_B200_LIB") or os.path.join(_HERE, "libdasp_b200.so")
 
 
 def build(verbose: bool = False) -> str:
