@@ -172,6 +172,14 @@ int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *strea
     return launch_spmv(h, d_x, d_y, h->L.order_rid, (cudaStream_t)stream);
 }
 
+int dasp_spmv_f16_f32out(dasp_handle *h, const void *d_x, float *d_y, int permuted, void *stream)
+{
+    if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_f16_f32out: NULL argument"); return DASP_ERR_INVALID; }
+    if (h->dtype != DASP_F16) { set_error("dasp_spmv_f16_f32out: the handle is not FP16"); return DASP_ERR_INVALID; }
+    DASP_ON_DEVICE(h->device);
+    return launch_spmv(h, d_x, d_y, permuted ? nullptr : h->L.order_rid, (cudaStream_t)stream, nullptr, nullptr, true);
+}
+
 int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, void *d_y, int permuted, void *stream)
 {
     if (!h || (!d_x && h->L.s.n > 0) || (!d_y && h->L.s.m > 0)) { set_error("dasp_spmv_axpby: NULL argument"); return DASP_ERR_INVALID; }

@@ -208,7 +208,7 @@ struct ScatterTo {
     const double *norm2;
 };
 int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st,
-                const double *alpha_beta = nullptr, const ScatterTo *multi = nullptr);
+                const double *alpha_beta = nullptr, const ScatterTo *multi = nullptr, bool out_f32 = false);
 int save_layout(const dasp_handle *h, const char *path);
 int load_layout(dasp_handle *h, const char *path);
 int launches_per_spmv(const dasp_handle *h);

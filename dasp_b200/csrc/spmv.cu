@@ -46,6 +46,7 @@ struct SpmvArgs {
     const int *scatter; // nullptr: permuted order
     double alpha, beta; // y = alpha*A*x + beta*y when axpby != 0
     int axpby;
+    int out_f32; // FP16 matrices only: y (and the extra destinations) are float, not half
     // fused exchange (dasp_spmv_scatter_to): the result is also stored into n_extra more vectors (peer GPUs' copies of
     // the next x, or one NVSwitch multicast mapping), at element offset row_offset, scaled by 1/sqrt(*rs_ptr)
     void *y_extra[7];
@@ -225,20 +226,35 @@ template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(co
     return to_acc(__ldg(x + c));
 }
 
+// element `idx` of an output vector: the handle's value type, or float for an FP16 matrix asked for FP32 output
+template <typename T> __device__ __forceinline__ void put(const SpmvArgs &a, void *base, long idx, typename Acc<T>::type v)
+{
+    if constexpr (sizeof(T) == 2) {
+        if (a.out_f32) { static_cast<float *>(base)[idx] = v; return; }
+    }
+    from_acc(static_cast<T *>(base) + idx, v);
+}
+template <typename T> __device__ __forceinline__ typename Acc<T>::type get(const SpmvArgs &a, const void *base, long idx)
+{
+    if constexpr (sizeof(T) == 2) {
+        if (a.out_f32) return static_cast<const float *>(base)[idx];
+    }
+    return to_acc(static_cast<const T *>(base)[idx]);
+}
+
 template <typename T>
 __device__ __forceinline__ void store_y(const SpmvArgs &a, long idx, typename Acc<T>::type v)
 {
     using A = typename Acc<T>::type;
-    T *y = static_cast<T *>(a.y);
     if (a.scatter) idx = a.scatter[idx];
     if (a.axpby) { // one flag for every non-default form: alpha/beta, 1/sqrt(norm^2) scaling, offset, extra destinations
-        v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * to_acc(y[idx]) : A(0));
+        v = (A)a.alpha * v + (a.beta != 0.0 ? (A)a.beta * get<T>(a, a.y, idx) : A(0));
         if (a.rs_ptr) v *= (A)rsqrt(__ldg(a.rs_ptr));
         idx += a.row_offset;
 #pragma unroll 1
-        for (int p = 0; p < a.n_extra; p++) from_acc(static_cast<T *>(a.y_extra[p]) + idx, v); // P2P / multicast stores
+        for (int p = 0; p < a.n_extra; p++) put<T>(a, a.y_extra[p], idx, v); // P2P / multicast stores
     }
-    from_acc(y + idx, v);
+    put<T>(a, a.y, idx, v);
 }
 
 template <typename A> __device__ __forceinline__ A warp_sum(A v)
@@ -1388,7 +1404,7 @@ int scale_by_rsqrt(double *d_v, int64_t count, const double *d_norm2, cudaStream
 }
 
 int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, cudaStream_t st, const double *alpha_beta,
-                const ScatterTo *multi)
+                const ScatterTo *multi, bool out_f32)
 {
     const Layout &L = h->L;
     const dasp_stats_t &s = L.s;
@@ -1396,6 +1412,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     SpmvArgs a{};
     a.x = d_x; a.y = d_y; a.scatter = scatter;
     a.axpby = (alpha_beta || multi) ? 1 : 0;
+    a.out_f32 = (out_f32 && h->dtype == DASP_F16) ? 1 : 0;
     a.alpha = alpha_beta ? alpha_beta[0] : 1.0;
     a.beta = alpha_beta ? alpha_beta[1] : 0.0;
     if (multi) {

@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         L.dasp_inverse_order.argtypes = [vp, C.POINTER(vp)]
         L.dasp_spmv_host_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
         L.dasp_spmv_axpby.argtypes = [vp, C.c_double, vp, C.c_double, vp, ip, vp]
+        L.dasp_spmv_f16_f32out.argtypes = [vp, vp, vp, ip, vp]
         L.dasp_save.argtypes = [vp, C.c_char_p]
         L.dasp_load.argtypes = [C.POINTER(vp), C.c_char_p, ip]
         L.dasp_spmv_timed.argtypes = [vp, vp, vp, vp, ip, ip, C.POINTER(C.c_float)]
@@ -177,6 +178,11 @@ class Dasp:
         """y = alpha*A*x + beta*y."""
         _check(load().dasp_spmv_axpby(self._h, alpha, _ptr(d_x), beta, _ptr(d_y), 1 if permuted else 0, C.c_void_p(stream)),
                "dasp_spmv_axpby")
+
+    def spmv_f32out(self, d_x, d_y_f32, permuted: bool = True, stream: int = 0) -> None:
+        """FP16 matrix and x, y stored as float32 (the fp32 accumulator, unrounded)."""
+        _check(load().dasp_spmv_f16_f32out(self._h, _ptr(d_x), _ptr(d_y_f32), 1 if permuted else 0, C.c_void_p(stream)),
+               "dasp_spmv_f16_f32out")
 
     def save(self, path: str) -> None:
         _check(load().dasp_save(self._h, os.fsencode(path)), "dasp_save")

@@ -127,6 +127,11 @@ int dasp_spmv_unpermuted(dasp_handle *h, const void *d_x, void *d_y, void *strea
  * src/main_f64.cu:23-24).  Rows without entries become beta*y. */
 int dasp_spmv_axpby(dasp_handle *h, double alpha, const void *d_x, double beta, void *d_y, int permuted, void *stream);
 
+/* FP16 matrix and x in, FP32 y out: the kernels accumulate an FP16 product in fp32 anyway; this entry
+ * stores that sum unrounded (d_y: m floats; permuted != 0: the reference's permuted order, else original row order).  The
+ * reference rounds to half (and accumulates in half, src/dasp_f16.h:121-126).  FP16 handles only. */
+int dasp_spmv_f16_f32out(dasp_handle *h, const void *d_x, float *d_y, int permuted, void *stream);
+
 /* Checkpoint of the preprocessed matrix (the layout is a pure function of the CSR): write every array and scalar of
  * the handle to one binary file / rebuild a handle from it on `device` without the CSR and without preprocessing. */
 int dasp_save(const dasp_handle *h, const char *path);

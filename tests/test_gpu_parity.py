@@ -481,3 +481,39 @@ def test_reference_main_linked_against_the_shim(cuda_device, tmp_path, prec):
         assert "cusparse:" in p.stdout
     rec = open(tmp_path / "data" / ("spmv_f64_record.csv" if prec == "double" else "spmv_f16_record.csv")).read().strip().splitlines()
     assert len(rec) == len(files) + 1
+
+
+@pytest.mark.parametrize("name", ["mixed_f1", "powerlaw_20k", "stencil27_12"])
+def test_fp16_in_fp32_out(dasp, cuda_device, name):
+    """FP16 matrix and x, FP32 y: the unrounded fp32 accumulator, permuted and original order; much closer to
+    the double-precision product of the half inputs than the half-rounded y, and rounding it to half reproduces dasp_spmv."""
+    import torch
+
+    m, n, rp, ci, v = get(name)
+    v = v.astype(np.float16)
+    x = x_for(n).astype(np.float16)
+    y_ref = oracle.csr_spmv_f16(m, rp, ci, v, x)
+    h = dasp.Dasp(oracle.F16, m, n, rp, ci, v)
+    h.set_variant(0, dasp.VARIANT_CUDA_CORE, 0)
+    order = h.export("order_rid")
+    s = torch.cuda.current_stream().cuda_stream
+    dx = torch.from_numpy(x).to(cuda_device)
+    y16 = torch.zeros(m, dtype=torch.float16, device=cuda_device)
+    y32 = torch.full((m,), float("nan"), dtype=torch.float32, device=cuda_device)
+    y32o = torch.full((m,), float("nan"), dtype=torch.float32, device=cuda_device)
+    h.spmv(dx, y16, s)
+    h.spmv_f32out(dx, y32, True, s)
+    h.spmv_f32out(dx, y32o, False, s)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(y32.to(torch.float16), y16))
+    assert bool(torch.equal(y32o[torch.from_numpy(order).to(cuda_device).long()], y32))
+    err32 = _rel_l2(y32.cpu().numpy(), y_ref[order])
+    err16 = _rel_l2(y16.cpu().numpy(), y_ref[order])
+    assert err32 <= 2e-6 and err32 < err16
+    h.close()
+    with pytest.raises(dasp.DaspError):
+        h64 = dasp.Dasp(oracle.F64, m, n, rp, ci, v.astype(np.float64))
+        try:
+            h64.spmv_f32out(dx, y32, True, s)
+        finally:
+            h64.close()
