@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5", "c3_spec", "c5_spec"])
     ap.add_argument("--grid", type=int, default=256, help="c4: stencil grid edge")
     ap.add_argument("--scale", type=float, default=1.0, help="c3/c5: fraction of the named size")
-    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split", "tma", "blocked", "banded", "nobands"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "cuda", "mma", "split", "tma", "blocked", "banded", "nobands", "mband", "sband"])
     ap.add_argument("--no-secondary", action="store_true", help="skip cuSPARSE / reference-kernel comparison")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cold", action="store_true", help="flush L2 before every timed launch (small workloads)")
@@ -331,9 +331,11 @@ def run_ours(args):
     h = dasp_b200.Dasp(dtype, r1 - r0, n, rp, ci, v, device=local, nnz=nnz)
     create_s = time.perf_counter() - t0
     st = h.stats()
-    var = {"auto": 0, "cuda": 1, "mma": 2, "split": 3, "tma": 4, "blocked": 5, "banded": 6, "nobands": 7}[args.variant]
-    # (medium, long, short); "nobands" = AUTO everywhere except short rows in the fused kernel (A/B aid for the band kernel)
-    h.set_variant(0 if var in (4, 5, 6, 7) else var, 0 if var in (3, 6, 7) else var, {2: 2, 6: 6, 7: 1, 1: 1}.get(var, 0))
+    # (medium, long, short) variants; A/B aids for the band kernels: "banded" forces both, "mband" / "sband" one of them
+    # (the other category in the fused kernel), "nobands" neither; the long rows stay AUTO in all four
+    triples = {"auto": (0, 0, 0), "cuda": (1, 1, 1), "mma": (2, 2, 2), "split": (3, 0, 0), "tma": (0, 4, 0), "blocked": (0, 5, 0),
+               "banded": (6, 0, 6), "nobands": (1, 0, 1), "mband": (6, 0, 1), "sband": (1, 0, 6)}
+    h.set_variant(*triples[args.variant])
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
@@ -498,7 +500,9 @@ def run_ours(args):
                        "row_long": st["row_long"], "row_block": st["row_block"], "short_rows": st["short_row_1"] + 2 * st["common_13"] + st["short_row_34"] + st["short_row_2"],
                        "device_bytes": st["device_bytes"], "long_gather_lines": st["long_gather_lines"],
                        "long_rows_column_blocked": bool(st["long_blocked"]), "short_rows_banded": bool(st["short_banded"]),
-                       "short_band_hit_rate": st["short_band_hit_rate"], "launches_per_spmv": h.launches_per_spmv()},
+                       "short_band_hit_rate": st["short_band_hit_rate"], "medium_rows_banded": bool(st["medium_banded"]),
+                       "medium_band_hit_rate": st["medium_band_hit_rate"], "medium_gather_lines": st["medium_gather_lines"],
+                       "launches_per_spmv": h.launches_per_spmv()},
         "parity_check_rel_l2": chk,
     }
     if breakdown:

@@ -116,6 +116,12 @@ struct Layout {
     int *short_map = nullptr;               // [short_map_n] category << 28 | CTA index inside the category
     int short_map_n = 0;
     int short_ctas[4] = {0, 0, 0, 0};       // CTAs of singles / 1&3 / 3&4 / 2&2 the map was built for
+    // Medium-band kernel: first column of the x window of every CTA (8 consecutive groups of the processing order), the
+    // fraction of the medium entries inside their CTA's window, and the average number of distinct 128-byte lines one
+    // 32-lane gather of the lane-per-row mapping touches (1-3 for a stencil, ~32 for scattered columns)
+    int *mb_lo = nullptr;
+    int mb_auto = 0;
+    double mb_hit_rate = 0.0, med_gather_lines = 0.0;
     // Short-band kernel: warp items of the four short segments sorted by the band of original rows they start in, and the
     // x window of every band
     int *sb_item = nullptr;                 // [sb_nitems] segment (2..5) << 28 | warp item inside the segment
@@ -143,6 +149,7 @@ struct Layout {
 
 struct dasp_handle {
     int device = 0;
+    int mb_attr_set = 0;
     int sb_attr_set = 0;
     int lcb_attr_set = 0; // lcb_kernel dynamic shared memory attribute set on this device
     int lcb_auto = 0; // AUTO uses the column-blocked long-row kernel (decided in derive() from long_lines_avg)
@@ -182,6 +189,7 @@ constexpr int LCB_PART = DASP_LCB_PART;     // most entries one CTA of the colum
 constexpr int LCB_COPIES = DASP_LCB_COPIES;       // private copies of the long-row accumulators (CTA c adds into copy c % 8): with one copy
                                     // every atomic of the GPU lands on row_long * 8 bytes, a handful of L2 lines
 constexpr int LCB_BYTES = 65536;    // shared-memory bytes of one staged block of x
+constexpr int MB_WINDOW_BYTES = 65536; // bytes of x one CTA of the medium-band kernel stages (must match spmv.cu MB_WIN_BYTES)
 constexpr int SB_BAND_ROWS = 16384; // original rows per band of the short-band kernel
 constexpr int SB_WINDOW_BYTES = 196608; // bytes of x one band stages in shared memory: 24576 doubles = the band + 4096 columns either side
 
@@ -193,6 +201,7 @@ int radix_sort_pairs(DevicePool &tmp, const int *keys_in, const int *vals_in, in
 int derive(dasp_handle *h, cudaStream_t st);
 int build_lcb(dasp_handle *h, cudaStream_t st);
 int build_short_bands(dasp_handle *h, cudaStream_t st, bool force);
+int build_medium_bands(dasp_handle *h, cudaStream_t st);
 // kernel-facing column indices := new_index[reference column]; compact indices and the column-blocked copy are rebuilt
 int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStream_t st);
 // range / monotonicity check of the offset and index arrays of a layout read from a file (dasp_load)

@@ -178,6 +178,83 @@ __global__ void short_cta_keys(const int *__restrict__ order_rid, ShortOrderGeom
     val[i] = ((c + 2) << 28) | local;
 }
 
+// ---- medium-band kernel: x window per CTA (8 consecutive groups of the processing order) ----------------------------
+// One CTA per chunk of 8 groups (256 rows).  Every row contributes the column of its first entry as a sample; the window
+// is centred on the MEDIAN sample (robust against the scattered columns a power-law row mixes into its window).
+// The same pass counts, for the first gather instruction of every group (tile 0, element 0), how many distinct 128-byte
+// lines of x its 32 lanes touch.
+__global__ void __launch_bounds__(256) mb_place(const int *__restrict__ order, int ngroups4, int row_block, const int *__restrict__ blockPtr,
+                                                const int *__restrict__ reg_cid, const int *__restrict__ irreg_rpt,
+                                                const int *__restrict__ irreg_cid, int esz, int wcap, int ncols, int *__restrict__ mb_lo,
+                                                unsigned long long *__restrict__ lines)
+{
+    __shared__ int samp[256];
+    __shared__ int med;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int item = blockIdx.x * 8 + warp;
+    int sample = INT32_MAX;
+    if (item < ngroups4) {
+        const int G = order ? order[item] : item;
+        const int g = 32 * G + lane;
+        if (g < row_block) {
+            const int b = g >> 3, r = g & 7;
+            const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
+            if (bp1 > bp0) sample = reg_cid[bp0 + 4 * r];
+            else if (irreg_rpt[g + 1] > irreg_rpt[g]) sample = irreg_cid[irreg_rpt[g]];
+        }
+        // distinct lines among the 32 lanes of this gather
+        const int line = sample == INT32_MAX ? -1 - lane : (int)(((long)sample * esz) >> 7);
+        const unsigned peers = __match_any_sync(0xffffffffu, line);
+        const unsigned leaders = __ballot_sync(0xffffffffu, (peers & ((1u << lane) - 1u)) == 0 && sample != INT32_MAX);
+        if (lane == 0) atomicAdd(lines, ((unsigned long long)__popc(leaders) << 32) | 1ull); // sum of lines in the high word, gathers in the low
+    }
+    samp[tid] = sample;
+    if (tid == 0) med = 0;
+    __syncthreads();
+    int valid = 0, rank = 0;
+    for (int k = 0; k < 256; k++) {
+        const int v = samp[k];
+        valid += v != INT32_MAX;
+        rank += (v < sample) || (v == sample && k < tid);
+    }
+    if (sample != INT32_MAX && rank == valid / 2) med = sample;
+    __syncthreads();
+    if (tid == 0) {
+        long lo = (long)med - wcap / 2;
+        if (lo > (long)ncols - wcap) lo = (long)ncols - wcap;
+        if (lo < 0) lo = 0;
+        mb_lo[blockIdx.x] = (int)(lo & ~7L);
+    }
+}
+
+// entries of the chunk inside / outside its window (regular tiles without padding, irregular tails)
+template <typename T>
+__global__ void __launch_bounds__(256) mb_hits(const int *__restrict__ order, int ngroups4, int row_block, const int *__restrict__ blockPtr,
+                                               const int *__restrict__ reg_cid, const T *__restrict__ reg_val, const int *__restrict__ irreg_rpt,
+                                               const int *__restrict__ irreg_cid, const int *__restrict__ mb_lo, int wcap,
+                                               unsigned long long *__restrict__ counts)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int item = blockIdx.x * 8 + warp;
+    if (item >= ngroups4) return;
+    const int G = order ? order[item] : item;
+    const int g = 32 * G + lane;
+    const int lo = mb_lo[blockIdx.x];
+    int in = 0, all = 0;
+    if (g < row_block) {
+        const int b = g >> 3, r = g & 7;
+        const int bp0 = blockPtr[b], bp1 = blockPtr[b + 1];
+        for (int p = bp0 + 4 * r; p < bp1; p += 32)
+            for (int e = 0; e < 4; e++) {
+                const int c = reg_cid[p + e];
+                if (!(c == 0 && reg_val[p + e] == T(0))) { all++; in += (unsigned)(c - lo) < (unsigned)wcap; }
+            }
+        for (int i = irreg_rpt[g]; i < irreg_rpt[g + 1]; i++) { all++; in += (unsigned)(irreg_cid[i] - lo) < (unsigned)wcap; }
+    }
+    for (int o = 16; o; o >>= 1) { in += __shfl_xor_sync(0xffffffffu, in, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+    if (lane == 0) { atomicAdd(counts, (unsigned long long)in); atomicAdd(counts + 1, (unsigned long long)all); }
+}
+
 // ---- short-band kernel: warp items of the short segments by row band, x window per band --------------------------
 struct SbGeom {
     int items[4];   // warp items of singles, 1&3, 3&4, 2&2 (as the fused kernel counts them)
@@ -628,6 +705,45 @@ int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long lon
 
 } // namespace
 
+int build_medium_bands(dasp_handle *h, cudaStream_t st)
+{
+    Layout &L = h->L;
+    const dasp_stats_t &s = L.s;
+    DevicePool &pool = h->pool;
+    DevicePool tmp;
+    struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
+    if (L.mb_lo) { pool.release(L.mb_lo); L.mb_lo = nullptr; }
+    L.mb_auto = 0; L.mb_hit_rate = 0.0; L.med_gather_lines = 0.0;
+    L.s.medium_banded = 0; L.s.medium_band_hit_rate = 0.0; L.s.medium_gather_lines = 0.0;
+    const int ngroups4 = s.blocknum / 4;
+    if (ngroups4 == 0 || s.row_block == 0) return DASP_OK;
+    const int nchunks = ceil_div(ngroups4, 8), esz = (int)L.esz, wcap = MB_WINDOW_BYTES / esz;
+    DASP_TRY(pool.alloc((void **)&L.mb_lo, sizeof(int) * (size_t)nchunks));
+    unsigned long long *counts = nullptr, hc[3] = {0, 0, 0};
+    DASP_TRY(tmp.alloc((void **)&counts, sizeof(unsigned long long) * 3));
+    DASP_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 3, st));
+    mb_place<<<nchunks, 256, 0, st>>>(L.med_order, ngroups4, s.row_block, L.blockPtr, L.k_reg_cid, L.irreg_rpt, L.k_irreg_cid, esz, wcap,
+                                      L.x_len, L.mb_lo, counts + 2);
+    if (h->dtype == DASP_F16)
+        mb_hits<unsigned short><<<nchunks, 256, 0, st>>>(L.med_order, ngroups4, s.row_block, L.blockPtr, L.k_reg_cid,
+                                                         (const unsigned short *)L.reg_val, L.irreg_rpt, L.k_irreg_cid, L.mb_lo, wcap, counts);
+    else
+        mb_hits<double><<<nchunks, 256, 0, st>>>(L.med_order, ngroups4, s.row_block, L.blockPtr, L.k_reg_cid, (const double *)L.reg_val,
+                                                 L.irreg_rpt, L.k_irreg_cid, L.mb_lo, wcap, counts);
+    DASP_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    DASP_CUDA(cudaStreamSynchronize(st));
+    DASP_CUDA(cudaGetLastError());
+    L.mb_hit_rate = hc[1] ? (double)hc[0] / (double)hc[1] : 0.0;
+    const unsigned long long gathers = hc[2] & 0xffffffffull, lsum = hc[2] >> 32;
+    L.med_gather_lines = gathers ? (double)lsum / (double)gathers : 0.0;
+    // worth it when the gathers are scattered (a stencil's coalesce on their own) and most of them hit the window
+    // (measured crossover: profiles/r02/README.md)
+    L.mb_auto = L.med_gather_lines >= 12.0 && L.mb_hit_rate >= 0.5;
+    L.s.medium_banded = L.mb_auto; L.s.medium_band_hit_rate = L.mb_hit_rate; L.s.medium_gather_lines = L.med_gather_lines;
+    h->L.s.device_bytes = h->pool.bytes;
+    return DASP_OK;
+}
+
 int build_short_bands(dasp_handle *h, cudaStream_t st, bool force)
 {
     int rc = h->dtype == DASP_F16 ? build_short_bands_t<unsigned short>(h, st, force) : build_short_bands_t<double>(h, st, force);
@@ -692,6 +808,7 @@ int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStrea
     DASP_TRY(decide_long_variant(h, st, lines));
     if (h->var_long == DASP_VARIANT_BLOCKED && !L.lcb_val) DASP_TRY(build_lcb(h, st));
     DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
+    DASP_TRY(build_medium_bands(h, st));
     DASP_CUDA(cudaStreamSynchronize(st));
     h->L.s.device_bytes = h->pool.bytes;
     return DASP_OK;
@@ -811,6 +928,7 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(decide_long_variant(h, st, lines));
     // ---- short rows by row band ----
     DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
+    DASP_TRY(build_medium_bands(h, st));
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

@@ -90,6 +90,9 @@ struct SpmvArgs {
     void *lcb_acc;
     unsigned *lcb_done;
     int lcb_bw_log2, lcb_nblk, lcb_nctas, ncols;
+    // medium-band kernel (MB, derive.cu): first column of the x window of every CTA (8 groups in processing order)
+    const int *mb_lo;
+    int mb_wcap;
     // short-band kernel (SB, derive.cu): warp items of the four short segments sorted by row band
     const int *sb_item;     // segment << 28 | warp item inside the segment
     const int *sb_band_ptr; // [sb_nbands + 1] first item of every band
@@ -216,6 +219,7 @@ template <typename T> struct XWin {
     const T *xs;
     int lo;
     unsigned len;
+    uint32_t bar = 0; // mbarrier (shared-memory address) the window's TMA copies complete on; 0: the window is already there
 };
 template <typename T> __device__ __forceinline__ typename Acc<T>::type gather(const T *x, int c, const XWin<T> *w)
 {
@@ -478,14 +482,14 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
 // medium rows (row blocks)
 
 template <typename T, bool MMA, bool KEEP>
-__device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
+__device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
     using A = typename Acc<T>::type;
     const int lane = threadIdx.x & 31;
     if (w * 4 >= a.blocknum) return;
     // 32 rows = 4 blocks; large matrices walk the groups in order of the original id of their first row
-    const int group = (!KEEP && !MMA && a.med_order) ? __ldg(a.med_order + w) : (int)w;
+    const int group = (!MMA && a.med_order) ? __ldg(a.med_order + w) : (int)w; // (the launch passes med_order only where it is used)
     const T *x = static_cast<const T *>(a.x);
     const T *val = static_cast<const T *>(a.reg_val);
     const int g = group * 32 + lane;
@@ -571,6 +575,11 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
         const T *pv = val + bp0 + 4 * r;
         const int *pc = a.reg_cid + bp0 + 4 * r;
         const T *iv = static_cast<const T *>(a.irreg_val);
+        bool arrived = false; // medium-band kernel: the x window is being copied into shared memory while the tiles load
+        auto window_ready = [&]() {
+            if (win && win->bar && !arrived) mbar_wait(win->bar, 0);
+            arrived = true;
+        };
         const int nt = min((bp1 - bp0) >> 5, (int)__ldg(a.blk_live + b));
         // column indices of tile k: compact form (tile base + 16-bit offsets) unless a block of this warp is flagged
         // wide (warp-uniform choice: no divergence, one code path live at a time)
@@ -601,13 +610,14 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
                             base[j] = 0;
                         }
                     }
+                    if (k == 0) window_ready();
                     A xv[MED_TB][4];
 #pragma unroll
                     for (int j = 0; j < MED_TB; j++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const unsigned h16 = (e & 1) ? (d[j][e >> 1] >> 16) : (d[j][e >> 1] & 0xFFFFu);
-                            xv[j][e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16);
+                            xv[j][e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16, win);
                         }
 #pragma unroll
                     for (int j = 0; j < MED_TB; j++)
@@ -626,18 +636,20 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
                             for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
                         }
                     }
+                    if (k == 0) window_ready();
                     A xv[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; j++)
 #pragma unroll
-                        for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+                        for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e], win);
 #pragma unroll
                     for (int j = 0; j < 4; j++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
                 }
             }
-            for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
+            window_ready(); // rows without a regular tile reach their first gather here
+            for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
         } else {
             // Small, L2-resident matrices (latency-bound: one launch is a handful of dependent round trips): B
             // tiles per batch, two batches in flight, software pipelined by hand (the asm loads keep program order) so
@@ -664,7 +676,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
 #pragma unroll
                 for (int j = 0; j < B; j++)
 #pragma unroll
-                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e]);
+                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e], win);
 #pragma unroll
                 for (int j = 0; j < B; j++)
 #pragma unroll
@@ -681,6 +693,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
                 wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
             }
             pdl_wait(); // streams of the first batch are in flight; x and y may belong to the previous kernel
+            window_ready();
             for (int k = 0; k < nt; k += 2 * B) {
                 load(vb, cb, k + B);
                 consume(va, ca);
@@ -689,10 +702,10 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w)
             }
             A xw[IR];
 #pragma unroll
-            for (int j = 0; j < IR; j++) xw[j] = gather(x, wc[j]);
+            for (int j = 0; j < IR; j++) xw[j] = gather(x, wc[j], win);
 #pragma unroll
             for (int j = 0; j < IR; j++) acc += to_acc(wv[j]) * xw[j];
-            for (int i = lo + IR; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol));
+            for (int i = lo + IR; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
         }
         if (g < a.row_block) store_y<T>(a, (long)a.row_long + g, acc);
         return;
@@ -1231,6 +1244,54 @@ __global__ void __launch_bounds__(SB_THREADS, 1) sb_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// medium rows with the x window of the CTA staged in shared memory (MB).  In the lane-per-row mapping every gather
+// instruction touches 32 different rows; when their columns do not share cache lines the L1 retires ONE gather per clock
+// and SM from an L2-resident x (tools/gather_bench.cu), which is exactly what a small matrix like cop20k_A costs (2.6 M
+// gathers / 148 SMs = 9.1 us) and what caps the length-sorted medium rows of the power-law shape.  With the groups walked
+// in order of original row id (med_order) the 8 groups of a CTA sit in one band of the matrix; a ninth warp copies the
+// band's window of x (64 KB, placed on the median column of the CTA's rows by derive.cu) into shared memory with TMA bulk
+// copies while the eight consumer warps already load their tiles, and the gathers are served from shared memory (5 per
+// clock and SM); columns outside the window fall back to global memory.
+constexpr int MB_THREADS = CTA + 32;
+constexpr int MB_WIN_BYTES = MB_WINDOW_BYTES;
+
+template <typename T, bool KEEP>
+__global__ void __launch_bounds__(MB_THREADS, KEEP ? 2 : 3) mb_kernel(const __grid_constant__ SpmvArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    if constexpr (KEEP) pdl_launch_dependents();
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar0 = smem_u32(&bar);
+    XWin<T> win;
+    win.lo = __ldg(a.mb_lo + blockIdx.x);
+    const long room = (long)a.ncols - win.lo;
+    const long n = room < a.mb_wcap ? room : a.mb_wcap;
+    win.len = n > 0 ? (unsigned)(n & ~(long)(16 / sizeof(T) - 1)) : 0u;
+    win.xs = reinterpret_cast<const T *>(dyn_smem);
+    win.bar = bar0;
+    if (tid == CTA) { // producer: first lane of the ninth warp
+        mbar_init(bar0, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == WARPS) {
+        if (tid == CTA) {
+            if constexpr (KEEP) pdl_wait(); // x may be the previous product's y
+            uint64_t keep;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+            const uint32_t bytes = win.len * (uint32_t)sizeof(T), dst = smem_u32(dyn_smem);
+            mbar_expect_tx(bar0, bytes);
+            const T *x = static_cast<const T *>(a.x);
+            for (uint32_t off = 0; off < bytes; off += 32768u)
+                bulk_g2s(dst + off, reinterpret_cast<const char *>(x + win.lo) + off, min(32768u, bytes - off), bar0, keep);
+        }
+        return;
+    }
+    medium_rows<T, false, KEEP>(a, (long)blockIdx.x * WARPS + warp, &win);
+}
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- power-iteration helpers ---------------------------------------------------------------------
@@ -1322,6 +1383,12 @@ static bool lcb_selected(const dasp_handle *h)
            (h->var_long == DASP_VARIANT_BLOCKED || (h->var_long == DASP_VARIANT_AUTO && h->lcb_auto));
 }
 
+static bool mb_selected(const dasp_handle *h)
+{
+    return h->L.mb_lo != nullptr && h->L.s.blocknum > 0 &&
+           (h->var_medium == DASP_VARIANT_BANDED || (h->var_medium == DASP_VARIANT_AUTO && h->L.mb_auto));
+}
+
 static bool sb_selected(const dasp_handle *h)
 {
     return h->L.sb_nbands > 0 && h->L.sb_nitems > 0 &&
@@ -1332,7 +1399,8 @@ int launches_per_spmv(const dasp_handle *h)
 {
     // column-blocked long rows and band-staged short rows are launches of their own, followed by the fused kernel (which
     // also turns the long-row accumulators into y)
-    return 1 + (lcb_selected(h) ? 1 : 0) + (((h->category_mask & 4) && sb_selected(h)) ? 1 : 0);
+    return 1 + (lcb_selected(h) ? 1 : 0) + (((h->category_mask & 4) && sb_selected(h)) ? 1 : 0) +
+           (((h->category_mask & 2) && mb_selected(h)) ? 1 : 0);
 }
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
@@ -1465,8 +1533,8 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         else lcb_kernel<double><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
         DASP_CUDA(cudaGetLastError());
     }
-    const int on_long = cm & 1, on_med = (cm >> 1) & 1, on_zero = (cm >> 3) & 1;
-    int on_short = (cm >> 2) & 1;
+    const int on_long = cm & 1, on_zero = (cm >> 3) & 1;
+    int on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1;
     // short rows by row band with x staged in shared memory (its own launch, 192 KB of shared memory per SM)
     const bool use_sb = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
     if (use_sb) {
@@ -1493,6 +1561,37 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const bool mma_long = h->var_long == DASP_VARIANT_MMA && !use_lcb;
     const bool tma_long = h->var_long == DASP_VARIANT_TMA && !use_lcb;
     const bool mma_short = !f16 && h->var_short == DASP_VARIANT_MMA;
+    const bool keep_all = small && med != 1 && !mma_long && !tma_long && !mma_short;
+    // medium rows with the CTA's window of x in shared memory (its own launch: 64 KB of shared memory per CTA)
+    const bool use_mb = on_med && med == 0 && mb_selected(h) && ((uintptr_t)d_x & 15) == 0;
+    if (use_mb) {
+        a.mb_lo = L.mb_lo; a.mb_wcap = MB_WIN_BYTES / (f16 ? 2 : 8); a.ncols = L.x_len;
+        a.med_order = L.med_order; // may be null: identity
+        if (!h->mb_attr_set) {
+            DASP_CUDA(cudaFuncSetAttribute(mb_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(mb_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(mb_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_WIN_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(mb_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_WIN_BYTES));
+            h->mb_attr_set = 1;
+        }
+        const int mb_grid = cdiv(s.blocknum / 4, WARPS);
+        if (keep_all) { // small matrices: programmatic dependent launch, as the fused KEEP kernels
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(mb_grid); cfg.blockDim = dim3(MB_THREADS); cfg.dynamicSmemBytes = MB_WIN_BYTES; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (f16) DASP_CUDA(cudaLaunchKernelEx(&cfg, mb_kernel<__half, true>, a));
+            else DASP_CUDA(cudaLaunchKernelEx(&cfg, mb_kernel<double, true>, a));
+        } else {
+            if (f16) mb_kernel<__half, false><<<mb_grid, MB_THREADS, MB_WIN_BYTES, st>>>(a);
+            else mb_kernel<double, false><<<mb_grid, MB_THREADS, MB_WIN_BYTES, st>>>(a);
+        }
+        DASP_CUDA(cudaGetLastError());
+        a.med_order = nullptr;
+        on_med = 0; // the fused kernel skips the medium rows
+    }
     a.items[0] = on_long * (use_lcb ? (long)cdiv(s.row_long, 32) : (long)L.n_long_units); // LCB: one lane per long row turns its accumulator into y
     a.items[1] = on_med * (long)(med == 2 ? s.blocknum : s.blocknum / 4);
     a.items[2] = on_short * (long)cdiv(s.short_row_1, 32 * SINGLES_PER_THREAD);

@@ -29,7 +29,9 @@ class _Stats(C.Structure):
                 + [("rate_fill0", C.c_double), ("data_X", C.c_int64), ("data_X2", C.c_int64),
                    ("data_origin1", C.c_int64), ("preprocess_ms", C.c_double), ("device_bytes", C.c_int64),
                    ("col_min", C.c_int), ("col_max", C.c_int), ("long_gather_lines", C.c_double),
-                   ("long_blocked", C.c_int), ("short_banded", C.c_int), ("short_band_hit_rate", C.c_double)])
+                   ("long_blocked", C.c_int), ("short_banded", C.c_int), ("short_band_hit_rate", C.c_double),
+                   ("medium_gather_lines", C.c_double), ("medium_band_hit_rate", C.c_double), ("medium_banded", C.c_int),
+                   ("reserved_", C.c_int)])
 
 
 def stats_struct_size() -> int:

@@ -62,7 +62,10 @@ typedef enum {
     DASP_VARIANT_BLOCKED = 5,   /* long rows only: column-blocked copy of the long part, x blocks staged in shared memory by
                                    TMA bulk copies, atomic merge of the split rows; AUTO picks it when the long rows'
                                    gathers are scattered (built on demand otherwise; needs row_long <= 65535) */
-    DASP_VARIANT_BANDED = 6     /* short rows only: the warp items of the four short segments walked by band of original
+    DASP_VARIANT_BANDED = 6     /* medium rows: the 8 groups of a CTA (walked in order of original row id) gather from a
+                                   64 KB window of x that a ninth warp stages in shared memory with TMA bulk copies; AUTO
+                                   picks it when the gathers are scattered and mostly inside the window.
+                                   short rows: the warp items of the four short segments walked by band of original
                                    rows, the band's window of x staged in shared memory by TMA bulk copies (double
                                    buffered), gathers served from there; AUTO picks it for large short parts whose entries
                                    lie inside their band's window (short_band_hit_rate) */
@@ -98,6 +101,10 @@ typedef struct dasp_stats_t {
     int short_banded;         /* AUTO runs the short rows through the band kernel (x windows staged in shared memory) */
     double short_band_hit_rate; /* diagnostic: fraction of short-row entries whose column lies inside the window of
                                 its row band (0 when the short part is too small for the band kernel) */
+    double medium_gather_lines; /* diagnostic: distinct 128-byte lines of x per 32-lane gather of the medium rows
+                                (lane-per-row mapping): 1-3 for a stencil, ~32 for scattered columns */
+    double medium_band_hit_rate; /* fraction of medium-row entries inside the x window of their CTA (medium-band kernel) */
+    int medium_banded, reserved_; /* AUTO runs the medium rows through the medium-band kernel */
 } dasp_stats_t;
 
 /* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,
@@ -176,7 +183,7 @@ int dasp_report(const dasp_handle *h, const char *label, double spmv_ms, char *o
 int dasp_export(const dasp_handle *h, const char *name, void *host_dst, int64_t cap_bytes,
                 int64_t *bytes);
 
-/* medium: AUTO | CUDA_CORE | MMA | SPLIT;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA | BANDED
+/* medium: AUTO | CUDA_CORE | MMA | SPLIT | BANDED;  long_rows: AUTO | CUDA_CORE | MMA | TMA | BLOCKED;  short_rows: AUTO | CUDA_CORE | MMA | BANDED
  * (short-row MMA is FP64 only; values that do not apply to a category fall back to CUDA_CORE). */
 int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows, dasp_variant short_rows);
 

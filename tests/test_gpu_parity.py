@@ -68,9 +68,9 @@ def test_preprocessing_bit_exact_and_spmv(dasp, cuda_device, name, dtype):
         dx = torch.from_numpy(x).to(cuda_device)
         C_, M_, S_, T_, B_, N_ = (dasp.VARIANT_CUDA_CORE, dasp.VARIANT_MMA, dasp.VARIANT_SPLIT, dasp.VARIANT_TMA, dasp.VARIANT_BLOCKED,
                                   dasp.VARIANT_BANDED)
-        # (medium, long, short): medium cuda/mma/split; long cuda/mma/tma/blocked; short cuda/mma(FP64 only)/banded.
+        # (medium, long, short): medium cuda/mma/split/banded; long cuda/mma/tma/blocked; short cuda/mma(FP64 only)/banded.
         # FP16 MMA = HMMA m16n8k16 (medium and long rows); the last triple is also used for the original-order product below
-        triples = [(C_, C_, C_), (M_, M_, M_ if dtype == oracle.F64 else C_), (S_, C_, C_), (C_, T_, C_), (C_, C_, N_), (C_, B_, N_)]
+        triples = [(C_, C_, C_), (M_, M_, M_ if dtype == oracle.F64 else C_), (S_, C_, C_), (C_, T_, C_), (N_, C_, N_), (N_, B_, N_)]
         for variant in triples:
             h.set_variant(*variant)
             for rep in range(2):  # second call checks the self-resetting long-row counters / zero rows
