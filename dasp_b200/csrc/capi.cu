@@ -572,6 +572,10 @@ int dasp_set_variant(dasp_handle *h, dasp_variant medium, dasp_variant long_rows
         DASP_ON_DEVICE(h->device);
         DASP_TRY(build_short_bands(h, h->own_stream, true));
     }
+    if (medium == DASP_VARIANT_BANDED && !h->L.mb_lo) { // and the medium-band windows
+        DASP_ON_DEVICE(h->device);
+        DASP_TRY(build_medium_bands(h, h->own_stream));
+    }
     return DASP_OK;
 }
 

@@ -81,7 +81,9 @@ __global__ void compress_cid(const int *__restrict__ blockPtr, const int *__rest
     int nlive = 0; // tiles up to the last one that holds a non-zero value: the kernels stop there (the FP16 layout pads
                    // every block to a multiple of 4 tiles, src/dasp_f16.h:1356; a tile of zeros contributes nothing)
     for (int p = bp0; p < bp1; p += 32) {
-        if (__any_sync(0xffffffffu, reg_val[p + lane] != T(0))) nlive = ((p - bp0) >> 5) + 1;
+        if (sizeof(T) == 2) { // only the FP16 layout pads blocks with whole tiles; the FP64 kernels do not read `live`
+            if (__any_sync(0xffffffffu, reg_val[p + lane] != T(0))) nlive = ((p - bp0) >> 5) + 1;
+        } else nlive = ((p - bp0) >> 5) + 1;
         const int c = reg_cid[p + lane];
         int mn = c ? c : INT32_MAX, mx = c;
         for (int o = 16; o; o >>= 1) {
@@ -736,9 +738,11 @@ int build_medium_bands(dasp_handle *h, cudaStream_t st)
     L.mb_hit_rate = hc[1] ? (double)hc[0] / (double)hc[1] : 0.0;
     const unsigned long long gathers = hc[2] & 0xffffffffull, lsum = hc[2] >> 32;
     L.med_gather_lines = gathers ? (double)lsum / (double)gathers : 0.0;
-    // worth it when the gathers are scattered (a stencil's coalesce on their own) and most of them hit the window
-    // (measured crossover: profiles/r02/README.md)
-    L.mb_auto = L.med_gather_lines >= 12.0 && L.mb_hit_rate >= 0.5;
+    // Never chosen by AUTO: measured slower than the fused kernel's medium rows on every configuration (C1 10.7 vs 9.3 us,
+    // C2 11.3 vs 7.2 us, C3 medium part 0.38 vs 0.21 ms, C4 1.14 vs 0.80 ms; profiles/r02/README.md) - 72-96 registers and
+    // the window leave 16-22 % of the warp slots occupied, and the gathers become shared-memory wavefronts at the same
+    // one-per-lane rate.  DASP_VARIANT_BANDED keeps it selectable.
+    L.mb_auto = 0;
     L.s.medium_banded = L.mb_auto; L.s.medium_band_hit_rate = L.mb_hit_rate; L.s.medium_gather_lines = L.med_gather_lines;
     h->L.s.device_bytes = h->pool.bytes;
     return DASP_OK;
@@ -808,7 +812,8 @@ int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStrea
     DASP_TRY(decide_long_variant(h, st, lines));
     if (h->var_long == DASP_VARIANT_BLOCKED && !L.lcb_val) DASP_TRY(build_lcb(h, st));
     DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
-    DASP_TRY(build_medium_bands(h, st));
+    if (h->var_medium == DASP_VARIANT_BANDED) DASP_TRY(build_medium_bands(h, st)); // on demand only (never AUTO)
+    else if (L.mb_lo) { pool.release(L.mb_lo); L.mb_lo = nullptr; }
     DASP_CUDA(cudaStreamSynchronize(st));
     h->L.s.device_bytes = h->pool.bytes;
     return DASP_OK;
@@ -928,7 +933,8 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_TRY(decide_long_variant(h, st, lines));
     // ---- short rows by row band ----
     DASP_TRY(build_short_bands(h, st, h->var_short == DASP_VARIANT_BANDED));
-    DASP_TRY(build_medium_bands(h, st));
+    if (h->var_medium == DASP_VARIANT_BANDED) DASP_TRY(build_medium_bands(h, st)); // on demand only (never AUTO)
+    else if (L.mb_lo) { pool.release(L.mb_lo); L.mb_lo = nullptr; }
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

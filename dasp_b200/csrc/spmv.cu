@@ -580,7 +580,8 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
             if (win && win->bar && !arrived) mbar_wait(win->bar, 0);
             arrived = true;
         };
-        const int nt = min((bp1 - bp0) >> 5, (int)__ldg(a.blk_live + b));
+        // FP16 blocks are padded to 4 tiles (src/dasp_f16.h:1356): stop at the last tile that holds a value; FP64 blocks are not
+        const int nt = sizeof(T) == 2 ? min((bp1 - bp0) >> 5, (int)__ldg(a.blk_live + b)) : (bp1 - bp0) >> 5;
         // column indices of tile k: compact form (tile base + 16-bit offsets) unless a block of this warp is flagged
         // wide (warp-uniform choice: no divergence, one code path live at a time)
         const bool compact = __all_sync(0xffffffffu, a.blk_wide != nullptr && a.blk_wide[b] == 0);

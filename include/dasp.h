@@ -101,10 +101,10 @@ typedef struct dasp_stats_t {
     int short_banded;         /* AUTO runs the short rows through the band kernel (x windows staged in shared memory) */
     double short_band_hit_rate; /* diagnostic: fraction of short-row entries whose column lies inside the window of
                                 its row band (0 when the short part is too small for the band kernel) */
-    double medium_gather_lines; /* diagnostic: distinct 128-byte lines of x per 32-lane gather of the medium rows
-                                (lane-per-row mapping): 1-3 for a stencil, ~32 for scattered columns */
-    double medium_band_hit_rate; /* fraction of medium-row entries inside the x window of their CTA (medium-band kernel) */
-    int medium_banded, reserved_; /* AUTO runs the medium rows through the medium-band kernel */
+    double medium_gather_lines; /* diagnostic, filled when DASP_VARIANT_BANDED is selected for the medium rows: distinct
+                                128-byte lines of x per 32-lane gather (1-3 for a stencil, ~32 for scattered columns) */
+    double medium_band_hit_rate; /* same: fraction of medium-row entries inside the x window of their CTA */
+    int medium_banded, reserved_; /* always 0: AUTO never picks the medium-band kernel (measured slower everywhere) */
 } dasp_stats_t;
 
 /* Analyse: run the DASP preprocessing on the GPU (replaces the host code src/dasp_f64.h:499-1157,
