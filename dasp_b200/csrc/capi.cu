@@ -21,10 +21,29 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+int DevicePool::reserve(size_t n)
+{
+    if (n < (1u << 20)) return DASP_OK; // small analyses: individual allocations are cheap
+    if (getenv("DASP_NO_SLAB")) return DASP_OK; // A/B aid
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { cudaGetLastError(); return DASP_OK; } // best effort: alloc() falls back to its own cudaMalloc
+    slabs.push_back(p);
+    slab = (char *)p; slab_size = n; slab_used = 0;
+    return DASP_OK;
+}
+
 int DevicePool::alloc(void **p, size_t n)
 {
     *p = nullptr;
     size_t want = n ? n : 256; // zero-length arrays still get a valid, aligned pointer
+    const size_t carve = (want + 255) & ~(size_t)255;
+    if (slab && slab_used + carve <= slab_size) {
+        *p = slab + slab_used;
+        slab_used += carve;
+        bytes += (int64_t)want;
+        return DASP_OK;
+    }
     cudaError_t e = cudaMalloc(p, want);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu bytes) -> %s", want, cudaGetErrorString(e));
@@ -38,15 +57,19 @@ int DevicePool::alloc(void **p, size_t n)
 
 void DevicePool::release(void *p)
 {
+    if (!p) return;
     auto it = std::find(ptrs.begin(), ptrs.end(), p);
-    if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); }
+    if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); } // pieces carved from a slab stay until free_all()
 }
 
 void DevicePool::free_all()
 {
     for (void *p : ptrs) cudaFree(p);
+    for (void *p : slabs) cudaFree(p);
     ptrs.clear();
+    slabs.clear();
     bytes = 0;
+    slab = nullptr; slab_size = slab_used = 0;
 }
 
 static bool is_device_ptr(const void *p)

@@ -56,10 +56,18 @@ struct DeviceGuard {
 
 // Tracks every device allocation of a handle so destroy/fail paths free them all.
 struct DevicePool {
-    std::vector<void *> ptrs;
-    int64_t bytes = 0;
+    std::vector<void *> ptrs;  // individually cudaMalloc'ed arrays
+    std::vector<void *> slabs; // cudaMalloc'ed slabs (see reserve)
+    int64_t bytes = 0;        // bytes handed out
+    // One cudaMalloc that the following alloc() calls carve from (256-byte aligned pieces) while they fit: the ~40 arrays
+    // of one analysis cost three driver allocations instead of one each (cudaMalloc / cudaFree of large blocks are the
+    // bulk of dasp_create's time on the GPU).  Best effort: what does not fit is allocated on its own.
+    char *slab = nullptr;
+    size_t slab_size = 0, slab_used = 0;
+    int reserve(size_t n);
+    void close_slab() { slab = nullptr; slab_size = slab_used = 0; } // later alloc() calls allocate on their own (releasable)
     int alloc(void **p, size_t n);
-    void release(void *p);
+    void release(void *p); // frees an individually allocated array now; pieces carved from a slab stay until free_all()
     void free_all();
 };
 
@@ -69,6 +77,8 @@ struct LongUnit {
     int slot; // index into the partial-sum scratch (== unit id)
     int begin, end;
 };
+
+constexpr int SMQ_MAX = 512; // upper bound of the SM count the SM-affine queues are sized for
 
 struct Layout {
     dasp_stats_t s{};
@@ -113,6 +123,8 @@ struct Layout {
     // short segments interleaved, in order of the ORIGINAL id of their first row, so that at any time the resident CTAs
     // gather from one sliding window of x (every length class / short segment sweeps all of x on its own otherwise).
     int *med_order = nullptr;               // [blocknum / 4] group processed by the w-th medium warp
+    int *smq_cnt = nullptr;                 // [SMQ_MAX + 1] per-SM chunk counters + arrivals of the SM-affine medium-row queues
+                                            // (small matrices; self-resetting: the last CTA to take a chunk zeroes them)
     int *short_map = nullptr;               // [short_map_n] category << 28 | CTA index inside the category
     int short_map_n = 0;
     int short_ctas[4] = {0, 0, 0, 0};       // CTAs of singles / 1&3 / 3&4 / 2&2 the map was built for
@@ -150,6 +162,7 @@ struct Layout {
 struct dasp_handle {
     int device = 0;
     int mb_attr_set = 0;
+    int smq_attr_set = 0;
     int sb_attr_set = 0;
     int lcb_attr_set = 0; // lcb_kernel dynamic shared memory attribute set on this device
     int lcb_auto = 0; // AUTO uses the column-blocked long-row kernel (decided in derive() from long_lines_avg)

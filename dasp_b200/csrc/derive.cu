@@ -827,6 +827,7 @@ int derive(dasp_handle *h, cudaStream_t st)
     DevicePool tmp;
     struct Guard { DevicePool &p; ~Guard() { p.free_all(); } } guard{tmp};
     const int cl = s.row_long, cm = s.row_block, blocknum = s.blocknum, m = s.m;
+    tmp.reserve(16 * ((size_t)blocknum / 4 + (size_t)m / 64 + 8192) + (4u << 20)); // sort buffers of the two work lists + radix / scan scratch
     L.k_long_cid = L.long_cid; L.k_reg_cid = L.reg_cid; L.k_irreg_cid = L.irreg_cid; L.k_short_cid = L.short_cid;
     L.relabelled = 0;
     L.x_len = s.n;
@@ -924,11 +925,15 @@ int derive(dasp_handle *h, cudaStream_t st)
             DASP_TRY(radix_sort_pairs(tmp, k0, v0, k1, L.short_map, total, 31, false, st));
         }
     }
+    // ---- SM-affine medium-row queues of the small-matrix kernels (spmv.cu): counters start at zero, the kernel resets them ----
+    DASP_TRY(pool.alloc((void **)&L.smq_cnt, sizeof(int) * (SMQ_MAX + 1)));
+    DASP_CUDA(cudaMemsetAsync(L.smq_cnt, 0, sizeof(int) * (SMQ_MAX + 1), st));
     // ---- inverse permutation (dasp_unpermute_to, relabelled mode) ----
     DASP_TRY(pool.alloc((void **)&L.inv_order, sizeof(int) * (size_t)m));
     if (m > 0) invert_order<<<grid_for(m, 256), 256, 0, st>>>(L.order_rid, m, L.inv_order);
     DASP_CUDA(cudaGetLastError());
 
+    pool.close_slab(); // what follows may be rebuilt later (relabelled mode, variants on demand): allocated on its own
     // ---- scattered long rows: column-blocked copy ----
     DASP_TRY(decide_long_variant(h, st, lines));
     // ---- short rows by row band ----

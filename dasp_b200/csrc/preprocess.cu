@@ -12,6 +12,7 @@
 //   block_fill / long_warps -> scans                blockPtr, irreg_rpt, long_rpt_new      (P11,P12)
 //   pack_short / pack_long / pack_irreg / pack_reg  padded value+index streams             (P6,P11,P13,P14)
 //   build_order                                     order_rid                              (P10)
+#include <chrono>
 #include "dasp_internal.h"
 
 namespace dasp {
@@ -510,13 +511,27 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
 
     s.dtype = F16 ? DASP_F16 : DASP_F64; s.m = m; s.n = n; s.nnz = nnz;
     L.esz = sizeof(T);
+    // DASP_TRACE_PREPROCESS=1: host time of every phase on stderr (each mark synchronises the stream: a diagnostic, not a timing)
+    const bool trace = getenv("DASP_TRACE_PREPROCESS") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dasp preprocess] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = std::chrono::steady_clock::now();
+    };
 
     // ---- P1/P3: stable partition of the row ids by category ----
     const int ntiles = ceil_div(m > 0 ? m : 1, TILE_ROWS);
+    // scratch of the whole analysis in one allocation: cat_rid, the sorted medium ids / lengths, the radix sort's key and
+    // value buffers (6 arrays of <= m + 1 ints), tile histograms and scan partials
+    tmp.reserve(28 * ((size_t)m + 64) + sizeof(int) * (size_t)(NCAT + RS_BINS + 8) * ((size_t)ntiles + 64) + (4u << 20));
     int *tile_counts = nullptr, *cat_rid = nullptr;
     DASP_TRY(tmp.alloc((void **)&tile_counts, sizeof(int) * ((size_t)NCAT * ntiles + 1)));
     DASP_TRY(tmp.alloc((void **)&cat_rid, sizeof(int) * (size_t)(m + 1)));
     DASP_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int) * ((size_t)NCAT * ntiles + 1), st));
+    mark("scratch slab");
     int *vflags = nullptr;
     DASP_TRY(tmp.alloc((void **)&vflags, sizeof(int) * 4));
     const int vinit[3] = {0, INT32_MAX, -1};
@@ -567,6 +582,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     blocknum = ceil_div(blocknum, 4 * s.rowloop) * 4 * s.rowloop; // src/dasp_f64.h:1044-1045
     s.blocknum = blocknum;
 
+    mark("validate + classify");
     // ---- P8: stable descending sort of the medium rows by length ----
     int *ms = nullptr, *ml = nullptr;
     DASP_TRY(tmp.alloc((void **)&ms, sizeof(int) * (size_t)(cm + 1)));
@@ -580,6 +596,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         DASP_TRY(radix_sort_pairs(tmp, len_in, cat_rid + seg[CAT_MED], ml, ms, cm, end_bit, true, st));
     }
 
+    mark("sort medium rows");
     // ---- P12: block fill analysis -> blockPtr, irreg_rpt ; P11: long_rpt_new ----
     DASP_TRY(pool.alloc((void **)&L.blockPtr, sizeof(int) * (size_t)(blocknum + 1)));
     DASP_TRY(pool.alloc((void **)&L.irreg_rpt, sizeof(int) * (size_t)(cm + 1)));
@@ -611,7 +628,20 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     if ((int64_t)s.warp_number * LONGW > INT32_MAX) { set_error("padded long part exceeds 32-bit offsets"); return DASP_ERR_RANGE; }
     s.fill0_nnz_long = s.warp_number * LONGW;
 
-    // ---- allocate the packed streams ----
+    mark("block fill + scans");
+    // ---- allocate the packed streams (and what derive() adds to them) from one slab ----
+    {
+        const size_t ev = sizeof(T), ei = sizeof(int);
+        const size_t fl = (size_t)s.fill0_nnz_long, fr = (size_t)s.fill0_nnz_reg, fs = (size_t)s.fill0_nnz_short;
+        const size_t units = (size_t)s.warp_number / 32 + (size_t)cl + 1024; // estimate of the long-row work units
+        size_t need = (fl + fr + fs + (size_t)s.fill0_nnz_irreg) * (ev + ei) + (size_t)m * ei       // reference layout
+                      + fl * 2 + fl / 8 + fr * 2 + fr / 8                                          // compact indices
+                      + units * 24 + (size_t)cl * 8 + (size_t)blocknum * 4 + (size_t)cm / 32       // units, flags
+                      + (size_t)blocknum + (size_t)m * ei                                           // med_order, inv_order
+                      + (size_t)(m / 64 + 4096) * ei;                                               // short_map
+        need += 64 * 256 + (1u << 20);                                                              // alignment of ~40 pieces, slack
+        pool.reserve(need);
+    }
     DASP_TRY(pool.alloc(&L.long_val, sizeof(T) * (size_t)s.fill0_nnz_long));
     DASP_TRY(pool.alloc((void **)&L.long_cid, sizeof(int) * (size_t)s.fill0_nnz_long));
     DASP_TRY(pool.alloc(&L.reg_val, sizeof(T) * (size_t)s.fill0_nnz_reg));
@@ -621,6 +651,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_TRY(pool.alloc(&L.short_val, sizeof(T) * (size_t)s.fill0_nnz_short));
     DASP_TRY(pool.alloc((void **)&L.short_cid, sizeof(int) * (size_t)s.fill0_nnz_short));
     DASP_TRY(pool.alloc((void **)&L.order_rid, sizeof(int) * (size_t)m));
+    mark("layout slab + allocations");
     DASP_CUDA(cudaMemsetAsync(L.long_val, 0, sizeof(T) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.long_cid, 0, sizeof(int) * (size_t)s.fill0_nnz_long, st));
     DASP_CUDA(cudaMemsetAsync(L.short_val, 0, sizeof(T) * (size_t)s.fill0_nnz_short, st));
@@ -664,6 +695,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     if (m > 0) build_order<<<grid_for(m, 256), 256, 0, st>>>(cat_rid, ms, og, m, L.order_rid);
     DASP_CUDA(cudaGetLastError());
 
+    mark("zero fill + pack kernels");
     // nnz_long: sum of long row lengths = nnz - everything else is not derivable yet; compute from the CSR
     // identity nnz = nnz_long + nnz_short + origin_nnz_reg + nnz_irreg (src/dasp_f64.h:1091) needs nnz_long,
     // so reduce the long lengths on the device (tiny).
@@ -702,7 +734,9 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
     DASP_CUDA(cudaGetLastError());
     // everything the kernels read that is NOT part of the reference layout (work units, compact indices, column-blocked
     // copy of scattered long rows, inverse permutation) is derived from the arrays above; dasp_load runs the same step
+    mark("nnz_long + accounting");
     DASP_TRY(derive(h, st));
+    mark("derive");
     DASP_CUDA(cudaStreamSynchronize(st));
     DASP_CUDA(cudaGetLastError());
     return DASP_OK;

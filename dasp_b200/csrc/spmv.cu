@@ -39,6 +39,9 @@ constexpr int WARPS = CTA / 32;
 #ifndef MED_MINB
 #define MED_MINB 6 // CTAs per SM the large-matrix kernels are compiled for
 #endif
+#ifndef KEEP_MINB
+#define KEEP_MINB 3 // CTAs per SM the small-matrix (KEEP) kernels are compiled for (<= 80 registers)
+#endif
 
 struct SpmvArgs {
     const void *x;
@@ -73,6 +76,10 @@ struct SpmvArgs {
     const unsigned char *blk_wide;    // nullptr: compression off; else 1 = block reads reg_cid
     const unsigned short *blk_live;   // tiles of the block worth reading (trailing all-zero tiles dropped)
     const int *med_order;             // locality order of the 32-row groups (nullptr: identity)
+    // SM-affine queues (small matrices): the groups, in locality order, are cut into smq_n contiguous ranges (one per SM) of
+    // smq_k chunks of <= 8 groups; a medium CTA takes the next chunk of the SM it runs on (nullptr: CTA index = chunk)
+    int *smq_cnt;
+    int smq_n, smq_k;
     const int *short_map;             // locality order of the short CTAs: category << 28 | CTA inside it (nullptr: off)
     int row_long, row_block, blocknum;
     // short
@@ -481,7 +488,8 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
 // ------------------------------------------------------------------------------------------------
 // medium rows (row blocks)
 
-template <typename T, bool MMA, bool KEEP>
+// LEAN (with KEEP): the register-lean loop of the large matrices with the L2 policy and the dependent-launch wait of the small ones
+template <typename T, bool MMA, bool KEEP, bool LEAN = false>
 __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
@@ -587,7 +595,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
         const bool compact = __all_sync(0xffffffffu, a.blk_wide != nullptr && a.blk_wide[b] == 0);
         const unsigned short *pd = a.reg_cdelta + bp0 + 4 * r;
         const int *pb = a.reg_cbase + (bp0 >> 5);
-        if constexpr (!KEEP) {
+        if constexpr (!KEEP || LEAN) {
             // Large matrices (bandwidth-bound): four tiles (4 x (256-bit values + 128-bit indices)) in flight per
             // lane, consumed as they arrive (40 registers, 6 CTAs per SM); the last batch is predicated.
             if (compact) {
@@ -612,6 +620,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
                         }
                     }
                     if (k == 0) window_ready();
+                    if constexpr (KEEP) { if (k == 0) pdl_wait(); } // x may be the previous product's y
                     A xv[MED_TB][4];
 #pragma unroll
                     for (int j = 0; j < MED_TB; j++)
@@ -638,6 +647,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
                         }
                     }
                     if (k == 0) window_ready();
+                    if constexpr (KEEP) { if (k == 0) pdl_wait(); }
                     A xv[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; j++)
@@ -650,6 +660,7 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
                 }
             }
             window_ready(); // rows without a regular tile reach their first gather here
+            if constexpr (KEEP) pdl_wait();
             for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
         } else {
             // Small, L2-resident matrices (latency-bound: one launch is a handful of dependent round trips): B
@@ -987,8 +998,8 @@ template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false, int NT =
 __global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
-    if constexpr (KEEP) pdl_launch_dependents();
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
+    if constexpr (KEEP) pdl_launch_dependents();
     int cat = 0, first = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++)
@@ -1004,6 +1015,63 @@ __global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spm
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
     if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
     run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * (NT / 32) + warp, dyn_smem);
+}
+
+// Small matrices, medium rows by SM (DASP_SMQ=1; measured and NOT chosen by AUTO, see the end of this comment).  One product of an L2-resident matrix is bound by the
+// L2 -> SM sector rate (~6300 B/clk for the chip): next to the 12 bytes per entry of the streams every scattered x gather
+// moves its own 32-byte sector.  x itself is small; what an SM needs of it fits in its L1 if the SM works on NEIGHBOURING
+// rows.  So the chunks of 8 groups (one 32-row group per warp), in order of the original id of their first row, are dealt
+// smq_k consecutive chunks per SM - as many CTAs as are resident per SM at once - and a CTA asks for the next chunk of the
+// SM it happens to run on (%smid); the chunks beyond smq_n * smq_k are taken by block index.  A CTA whose SM has no chunk
+// left looks for a queue that has (one warp reads 32 counters per round trip).  Exactly one CTA per chunk is launched, so
+// every chunk is taken once.  The last CTA to take its chunk zeroes the counters for the next launch, and only then lets
+// the dependent launch start.
+// Measured (profiles/r02/README.md §3): L1 hit rate 48 -> 64 % (FP16 81 %), L2 sectors per product 1.89 M -> 1.32 M, and yet
+// 12.9 vs 9.3 us (FP64) / 10.8 vs 7.2 us (FP16) back to back: the chunk hand-out and the order indirection add three dependent
+// round trips to a kernel that is six long, which costs more than the sectors saved.
+template <typename T, int MINB, bool LEAN>
+__global__ void __launch_bounds__(CTA, MINB) smq_kernel(const __grid_constant__ SpmvArgs a)
+{
+    __shared__ int s_chunk;
+    const int queued = a.smq_n * a.smq_k;
+    if ((int)blockIdx.x >= queued) {
+        if (threadIdx.x == 0) s_chunk = blockIdx.x;
+    } else if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int q = (int)(smid % (unsigned)a.smq_n), slot = 0;
+        if (lane == 0) slot = atomicAdd(a.smq_cnt + q, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        for (int tries = 0; slot >= a.smq_k; tries++) {
+            if (tries > a.smq_n) __trap(); // counters left over by an aborted / concurrent launch on this handle: fault, do not spin
+            // this SM's chunks are gone: find a queue that still has one, 32 queues per round trip starting after q
+            int found = -1;
+            for (int base = 1; base < a.smq_n && found < 0; base += 32) {
+                const int t = base + lane;
+                int qq = q + t;
+                if (qq >= a.smq_n) qq -= a.smq_n;
+                const bool free_slot = t < a.smq_n && *((volatile int *)a.smq_cnt + qq) < a.smq_k;
+                const unsigned m = __ballot_sync(0xffffffffu, free_slot);
+                if (m) found = __shfl_sync(0xffffffffu, qq, __ffs(m) - 1);
+            }
+            if (found < 0) found = q + 1 == a.smq_n ? 0 : q + 1; // (raced: somebody took it in between) try again
+            q = found;
+            if (lane == 0) slot = atomicAdd(a.smq_cnt + q, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        }
+        if (lane == 0) {
+            s_chunk = q * a.smq_k + slot;
+            if (atomicAdd(a.smq_cnt + SMQ_MAX, 1) == queued - 1) { // every queued CTA of this launch has its chunk
+                for (int i = 0; i < a.smq_n; i++) a.smq_cnt[i] = 0;
+                a.smq_cnt[SMQ_MAX] = 0;
+                __threadfence();
+            }
+        }
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    medium_rows<T, false, true, LEAN>(a, (long)s_chunk * (CTA / 32) + (threadIdx.x >> 5));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1396,12 +1464,30 @@ static bool sb_selected(const dasp_handle *h)
            (h->var_short == DASP_VARIANT_BANDED || (h->var_short == DASP_VARIANT_AUTO && h->L.sb_auto));
 }
 
+// small (L2-resident) matrix whose medium rows go through the SM-affine queue kernel (same conditions as launch_spmv)
+static bool smq_selected(const dasp_handle *h)
+{
+    static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
+    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 256;
+    const dasp_stats_t &s = h->L.s;
+    const bool small = s.data_X <= ((int64_t)48 << 20);
+    const bool plain = (h->var_medium == DASP_VARIANT_AUTO || h->var_medium == DASP_VARIANT_CUDA_CORE) &&
+                       h->var_long != DASP_VARIANT_MMA && h->var_long != DASP_VARIANT_TMA &&
+                       !(h->dtype != DASP_F16 && h->var_short == DASP_VARIANT_MMA);
+    return use_smq && keep_shape != 128 && small && plain && (h->category_mask & 2) && s.blocknum > 0 && h->L.smq_cnt != nullptr;
+}
+
 int launches_per_spmv(const dasp_handle *h)
 {
-    // column-blocked long rows and band-staged short rows are launches of their own, followed by the fused kernel (which
-    // also turns the long-row accumulators into y)
-    return 1 + (lcb_selected(h) ? 1 : 0) + (((h->category_mask & 4) && sb_selected(h)) ? 1 : 0) +
-           (((h->category_mask & 2) && mb_selected(h)) ? 1 : 0);
+    // column-blocked long rows, band-staged short / medium rows and the SM-affine medium rows of small matrices are launches of
+    // their own, followed by the fused kernel for whatever is left (it also turns the long-row accumulators into y)
+    const dasp_stats_t &s = h->L.s;
+    const int cm = h->category_mask;
+    const bool sb = (cm & 4) && sb_selected(h), mb = (cm & 2) && mb_selected(h), smq = !mb && smq_selected(h);
+    const bool short_rows = (long)s.short_row_1 + s.common_13 + s.short_row_34 + s.short_row_2 > 0;
+    const bool fused = ((cm & 1) && s.row_long > 0) || ((cm & 2) && s.blocknum > 0 && !mb && !smq) || ((cm & 4) && short_rows && !sb) ||
+                       ((cm & 8) && s.row_zero > 0);
+    return (fused ? 1 : 0) + (lcb_selected(h) ? 1 : 0) + (sb ? 1 : 0) + (mb ? 1 : 0) + (smq ? 1 : 0);
 }
 
 int sumsq(const double *d_v, int64_t count, double *d_out, cudaStream_t st)
@@ -1606,6 +1692,39 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 256;
     const bool narrow = keep && keep_shape == 128;
     const int nw = narrow ? 4 : WARPS;
+    // small matrices: medium rows handed out by SM (smq_kernel, its own launch)
+    static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
+    if (keep && use_smq && !narrow && med == 0 && a.items[1] > 0 && L.smq_cnt) {
+        static const int lean = getenv("DASP_SMQ_LEAN") ? atoi(getenv("DASP_SMQ_LEAN")) : 0; // A/B aid: 1 = register-lean loop, 4 CTAs per SM
+        const int resident = lean ? 4 : KEEP_MINB; // CTAs per SM the kernel is compiled for
+        const int chunks = cdiv(a.items[1], WARPS);
+        a.smq_n = min(h->sm_count > 0 ? h->sm_count : 148, SMQ_MAX);
+        a.smq_k = min(chunks / a.smq_n, resident); // chunks dealt by SM; the rest goes by block index
+        a.smq_cnt = L.smq_cnt;
+        a.med_order = L.med_order; // may be null: the layout order is already the local one
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(chunks); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (!h->smq_attr_set) {
+            cudaFuncSetAttribute(smq_kernel<double, KEEP_MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            cudaFuncSetAttribute(smq_kernel<__half, KEEP_MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            cudaFuncSetAttribute(smq_kernel<double, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            cudaFuncSetAttribute(smq_kernel<__half, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            h->smq_attr_set = 1;
+        }
+        if (lean) {
+            if (f16) DASP_CUDA(cudaLaunchKernelEx(&cfg, smq_kernel<__half, 4, true>, a));
+            else DASP_CUDA(cudaLaunchKernelEx(&cfg, smq_kernel<double, 4, true>, a));
+        } else {
+            if (f16) DASP_CUDA(cudaLaunchKernelEx(&cfg, smq_kernel<__half, KEEP_MINB, false>, a));
+            else DASP_CUDA(cudaLaunchKernelEx(&cfg, smq_kernel<double, KEEP_MINB, false>, a));
+        }
+        a.med_order = nullptr;
+        a.items[1] = 0; // the fused kernel skips the medium rows
+    }
     long total_items = 0;
     int acc_ctas = 0;
     for (int k = 0; k < 7; k++) {
