@@ -24,7 +24,8 @@ void set_error(const char *fmt, ...)
 int DevicePool::reserve(size_t n)
 {
     if (n < (1u << 20)) return DASP_OK; // small analyses: individual allocations are cheap
-    if (getenv("DASP_NO_SLAB")) return DASP_OK; // A/B aid
+    if (getenv("DASP_NO_SLAB")) return DASP_OK; // A/B aids
+    if (const char *e = getenv("DASP_SLAB_MAX_MB")) { if (n > ((size_t)atol(e) << 20)) return DASP_OK; }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) { cudaGetLastError(); return DASP_OK; } // best effort: alloc() falls back to its own cudaMalloc

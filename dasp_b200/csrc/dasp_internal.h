@@ -114,6 +114,7 @@ struct Layout {
     unsigned short *reg_cdelta = nullptr;  // [fill0_nnz_reg]
     unsigned char *blk_wide = nullptr;     // [blocknum] 1: some tile of the block spans >= 65535 columns -> use reg_cid
     unsigned short *blk_live = nullptr;    // [blocknum] tiles of the block up to the last one holding a non-zero value
+    int reg_compact_done = 0;              // the four arrays above were written by pack_reg (dasp_create); derive() skips compress_cid once
     int *long_cbase = nullptr;              // [fill0_nnz_long / 32] same compact form for the long part
     unsigned short *long_cdelta = nullptr;  // [fill0_nnz_long]
     unsigned char *long_wide = nullptr;     // [n_long_units] in execution order

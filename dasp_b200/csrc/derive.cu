@@ -666,7 +666,8 @@ int derive_indices(dasp_handle *h, cudaStream_t st, unsigned long long *lines)
         compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(
             L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.k_long_cid, L.n_long_units, longw, LONG_UNIT_WARPS, esz,
             L.long_cbase, L.long_cdelta, L.long_wide, lines);
-    if (blocknum > 0) {
+    if (L.reg_compact_done) L.reg_compact_done = 0; // written by pack_reg from the same indices (dasp_create): nothing to do this once
+    else if (blocknum > 0) {
         if (h->dtype == DASP_F16)
             compress_cid<unsigned short><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(
                 L.blockPtr, L.k_reg_cid, (const unsigned short *)L.reg_val, blocknum, L.reg_cbase, L.reg_cdelta, L.blk_wide, L.blk_live);
@@ -858,10 +859,12 @@ int derive(dasp_handle *h, cudaStream_t st)
     // ---- medium rows: irregular-tail flags, compact indices ----
     const int ngroups = ceil_div(cm, 32);
     DASP_TRY(pool.alloc((void **)&L.med_has_irreg, (size_t)ngroups));
-    DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
-    DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
-    DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
-    DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
+    if (!L.reg_cbase) { // (dasp_create has them already, filled by pack_reg; dasp_load comes here without)
+        DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
+        DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
+        DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
+        DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
+    }
     if (cm > 0) flag_irreg<<<grid_for(ngroups, 256), 256, 0, st>>>(L.irreg_rpt, cm, ngroups, L.med_has_irreg);
     DASP_TRY(derive_indices(h, st, lines));
     // ---- locality-ordered work lists (see dasp_internal.h) ----

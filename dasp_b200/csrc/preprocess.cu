@@ -218,11 +218,15 @@ __global__ void pack_irreg(const int *__restrict__ rowptr, const int *__restrict
 
 // P14: one warp per 8-row block; lane (r = lane/4, c = lane%4) writes slot k*32 + lane of the block:
 // tile-major 8x4 fragments, zero beyond the row's regular length (src/dasp_f64.h:1112-1157)
+// The warp holds the 32 column indices of a tile in registers, so it also writes the compact form the SpMV kernels read
+// (derive.cu: compress_cid is the same computation from reg_cid, used after dasp_load and for relabelled indices): per tile
+// the smallest non-zero column as base + 16-bit offsets (0xFFFF = column 0), per block the wide flag and the live tiles.
 template <typename T, bool F16>
 __global__ void pack_reg(const int *__restrict__ rowptr, const int *__restrict__ colidx, const T *__restrict__ val,
                          const int *__restrict__ ms, const int *__restrict__ ml, const int *__restrict__ blockPtr,
                          const int *__restrict__ irreg_rpt, int row_block, int blocknum, T *__restrict__ reg_val,
-                         int *__restrict__ reg_cid)
+                         int *__restrict__ reg_cid, int *__restrict__ cbase, unsigned short *__restrict__ cdelta,
+                         unsigned char *__restrict__ wide, unsigned short *__restrict__ live)
 {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= blocknum) return;
@@ -237,13 +241,30 @@ __global__ void pack_reg(const int *__restrict__ rowptr, const int *__restrict__
         if (reglen > Wb) reglen = Wb;
         src = (size_t)rowptr[ms[g]];
     }
+    bool any_wide = false;
+    int nlive = 0;
     for (int k = 0; k * 4 < Wb; k++) {
         int col = k * 4 + c;
         size_t slot = (size_t)bp + k * 32 + lane;
         bool ok = col < reglen;
-        reg_val[slot] = ok ? val[src + col] : T(0);
-        reg_cid[slot] = ok ? colidx[src + col] : 0;
+        const T v = ok ? val[src + col] : T(0);
+        const int cid = ok ? colidx[src + col] : 0;
+        reg_val[slot] = v;
+        reg_cid[slot] = cid;
+        if (F16) { if (__any_sync(0xffffffffu, v != T(0))) nlive = k + 1; } // (FP16 blocks are padded with whole tiles of zeros)
+        else nlive = k + 1;
+        int mn = cid ? cid : INT32_MAX, mx = cid;
+        for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == INT32_MAX) mn = 0; // tile of zeros only
+        const bool fits = (mx - mn) < 65535;
+        any_wide |= !fits;
+        cdelta[slot] = (unsigned short)(cid == 0 ? 0xFFFF : (fits ? cid - mn : 0));
+        if (lane == 0) cbase[slot >> 5] = mn;
     }
+    if (lane == 0) { wide[b] = any_wide ? 1 : 0; live[b] = (unsigned short)min(nlive, 65535); }
 }
 
 struct ShortGeom {
@@ -598,6 +619,7 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
 
     mark("sort medium rows");
     // ---- P12: block fill analysis -> blockPtr, irreg_rpt ; P11: long_rpt_new ----
+    pool.reserve(sizeof(int) * ((size_t)blocknum + cm + cl + 3) + 4 * 256); // the three offset arrays in one allocation
     DASP_TRY(pool.alloc((void **)&L.blockPtr, sizeof(int) * (size_t)(blocknum + 1)));
     DASP_TRY(pool.alloc((void **)&L.irreg_rpt, sizeof(int) * (size_t)(cm + 1)));
     DASP_TRY(pool.alloc((void **)&L.long_rpt_new, sizeof(int) * (size_t)(cl + 1)));
@@ -684,9 +706,18 @@ int run(dasp_handle *h, int m, int n, int64_t nnz, const int *rowptr, const int 
         pack_irreg<T><<<grid_for(cm, 256), 256, 0, st>>>(rowptr, colidx, val, ms, L.irreg_rpt, cm, (T *)L.irreg_val,
                                                           L.irreg_cid);
     }
-    if (blocknum > 0)
+    // (the compact index form of the regular part is written by the same pass; derive() finds it done)
+    DASP_TRY(pool.alloc((void **)&L.reg_cbase, sizeof(int) * (size_t)(s.fill0_nnz_reg / 32)));
+    DASP_TRY(pool.alloc((void **)&L.reg_cdelta, sizeof(unsigned short) * (size_t)s.fill0_nnz_reg));
+    DASP_TRY(pool.alloc((void **)&L.blk_wide, (size_t)blocknum));
+    DASP_TRY(pool.alloc((void **)&L.blk_live, sizeof(unsigned short) * (size_t)blocknum));
+    L.reg_compact_done = 0;
+    if (blocknum > 0) {
         pack_reg<T, F16><<<grid_for((long)blocknum * 32, 256), 256, 0, st>>>(rowptr, colidx, val, ms, ml, L.blockPtr, L.irreg_rpt,
-                                                                               cm, blocknum, (T *)L.reg_val, L.reg_cid);
+                                                                               cm, blocknum, (T *)L.reg_val, L.reg_cid, L.reg_cbase,
+                                                                               L.reg_cdelta, L.blk_wide, L.blk_live);
+        L.reg_compact_done = 1;
+    }
     // ---- P10: order_rid ----
     OrderGeom og;
     og.cl = cl; og.cm = cm; og.n1 = n1; og.c13 = c13; og.n3 = n3; og.c4 = c4; og.c2 = c2; og.c0 = c0;

@@ -517,3 +517,45 @@ def test_fp16_in_fp32_out(dasp, cuda_device, name):
             h64.spmv_f32out(dx, y32, True, s)
         finally:
             h64.close()
+
+
+_SMQ_SNIPPET = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, {tests!r}); sys.path.insert(0, {root!r})
+import dasp_b200, oracle
+from cases import get, x_for
+dasp_b200.load()
+dev = torch.device("cuda:0")
+for name in ("mixed_f1", "powerlaw_20k", "ragged_tail_blocks", "wide_span_mixed", "stencil27_12", "rowloop_59990"):
+    m, n, rp, ci, v = get(name)
+    for dtype, npdt, tdt, tol in ((oracle.F64, np.float64, torch.float64, 1e-12), (oracle.F16, np.float16, torch.float16, 2e-3)):
+        vv = v.astype(npdt); x = x_for(n).astype(npdt)
+        h = dasp_b200.Dasp(dtype, m, n, rp, ci, vv)
+        order = h.export("order_rid")
+        dx = torch.from_numpy(x).to(dev); dy = torch.zeros(m, dtype=tdt, device=dev)
+        want = (oracle.csr_spmv_f64 if dtype == oracle.F64 else oracle.csr_spmv_f16)(m, rp, ci, vv, x)[order]
+        for rep in range(3):  # the queue counters reset themselves: the second and third product must be right too
+            dy.fill_(7)
+            h.spmv(dx, dy, torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+            got = dy.cpu().numpy().astype(np.float64)
+            err = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-300)
+            assert err <= tol, (name, dtype, rep, err)
+        h.close()
+print("smq ok")
+"""
+
+
+@pytest.mark.parametrize("lean", ["0", "1"], ids=["pipelined", "lean"])
+def test_sm_affine_queue_variant(cuda_device, lean):
+    """smq_kernel (spmv.cu) is chosen by the environment only (measured slower than the fused kernel, never AUTO): run it
+    in a child process on small matrices of every category mix, three products in a row per handle."""
+    import os
+    import subprocess
+    import sys
+
+    tests = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DASP_SMQ="1", DASP_SMQ_LEAN=lean)
+    out = subprocess.run([sys.executable, "-c", _SMQ_SNIPPET.format(tests=tests, root=os.path.dirname(tests))],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "smq ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
