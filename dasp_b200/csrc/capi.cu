@@ -173,6 +173,9 @@ int dasp_destroy(dasp_handle *h)
     DeviceGuard guard(h->device);
     h->pool.free_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int k = 0; k < 3; k++) {
         if (h->batch_stream[k]) cudaStreamDestroy(h->batch_stream[k]);
         for (int b = 0; b < 2; b++)

@@ -181,6 +181,9 @@ struct dasp_handle {
     // device staging of x / y for dasp_spmv_host (owned by pool)
     void *dx_stage = nullptr, *dy_stage = nullptr;
     cudaStream_t own_stream = nullptr;
+    // column-blocked long rows run beside the fused kernel (launch_spmv): a side stream forked from / joined to the caller's
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // dasp_spmv_host_batch: upload / compute / download streams, double-buffered staging and hand-over events
     int batch_ready = 0;
     cudaStream_t batch_stream[3] = {nullptr, nullptr, nullptr};

@@ -1236,6 +1236,12 @@ template <typename T> __device__ __forceinline__ void lcb_finalize(const SpmvArg
     store_y<T>(a, r, t);
 }
 
+// the same as a launch of its own: used when the column-blocked kernel ran BESIDE the fused kernel (launch_spmv)
+template <typename T> __global__ void __launch_bounds__(256) lcb_finalize_kernel(const __grid_constant__ SpmvArgs a)
+{
+    lcb_finalize<T>(a, (long)blockIdx.x * 8 + (threadIdx.x >> 5));
+}
+
 // ------------------------------------------------------------------------------------------------
 // short rows by row band (SB): a scattered gather costs the L1 one wavefront per lane (measured: ~0.72 gathers per clock
 // and SM, which caps rows of 1-4 entries far below the HBM roofline).  Here the warp items of the four short segments
@@ -1612,16 +1618,56 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         a.lcb_cta_first = L.lcb_cta_first; a.lcb_acc = L.lcb_acc; a.lcb_done = L.lcb_done;
         a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = L.x_len;
         if (!h->lcb_attr_set) {
-            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
-            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, LCB_BYTES));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->lcb_attr_set = 1;
         }
-        if (f16) lcb_kernel<__half><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
-        else lcb_kernel<double><<<L.lcb_nctas, CTA, LCB_BYTES, st>>>(a);
-        DASP_CUDA(cudaGetLastError());
     }
-    const int on_long = cm & 1, on_zero = (cm >> 3) & 1;
+    int on_long = cm & 1;
+    const int on_zero = (cm >> 3) & 1;
     int on_med = (cm >> 1) & 1, on_short = (cm >> 2) & 1;
+    // The column-blocked kernel is bound by DRAM and the shared-memory gathers, the medium / short rows of the same matrix by
+    // the L1 miss path (one scattered gather per clock and SM): different resources, so the two launches run BESIDE each
+    // other - the column-blocked kernel on a side stream forked from the caller's, limited to `overlap` CTAs per SM by
+    // its shared-memory request so that CTAs of the fused kernel fit next to them, the long-row accumulators turned into y
+    // by a small launch after the join.  Not with the short-band kernel (192 KB of shared memory per SM).
+    static const int overlap_env = getenv("DASP_LCB_OVERLAP") ? atoi(getenv("DASP_LCB_OVERLAP")) : 0;
+    const bool sb_would_run = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
+    const int overlap = (use_lcb && on_long && !sb_would_run && (on_med || on_short)) ? overlap_env : 0;
+    bool joined_later = false;
+    if (use_lcb) {
+        cudaStream_t lcb_stream = st;
+        size_t lcb_smem = LCB_BYTES;
+        if (overlap > 0) {
+            if (!h->side_stream) {
+                DASP_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+                DASP_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                DASP_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+            }
+            DASP_CUDA(cudaEventRecord(h->ev_fork, st));
+            DASP_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            lcb_stream = h->side_stream;
+            if (overlap == 2) lcb_smem = 100 * 1024; // two CTAs per SM instead of three
+            else if (overlap == 1) lcb_smem = 200 * 1024;
+            joined_later = true;
+        }
+        if (f16) lcb_kernel<__half><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
+        else lcb_kernel<double><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
+        DASP_CUDA(cudaGetLastError());
+        if (joined_later) {
+            DASP_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+            on_long = 0; // the fused kernel does not touch the long rows; lcb_finalize_kernel does after the join
+        }
+    }
+    auto finish_overlap = [&]() -> int {
+        if (!joined_later) return DASP_OK;
+        DASP_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        const int nb = cdiv(s.row_long, 256);
+        if (f16) lcb_finalize_kernel<__half><<<nb, 256, 0, st>>>(a);
+        else lcb_finalize_kernel<double><<<nb, 256, 0, st>>>(a);
+        DASP_CUDA(cudaGetLastError());
+        return DASP_OK;
+    };
     // short rows by row band with x staged in shared memory (its own launch, 192 KB of shared memory per SM)
     const bool use_sb = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
     if (use_sb) {
@@ -1732,7 +1778,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         a.e[k] = acc_ctas;
         total_items += a.items[k];
     }
-    if (total_items == 0) return DASP_OK;
+    if (total_items == 0) return finish_overlap();
     const int grid = a.e[6];
     // locality-ordered work lists: large matrices, everything on, the CTA counts the lists were built for
     static const int use_order = getenv("DASP_NO_LOCALITY_ORDER") ? 0 : 1; // A/B aid
@@ -1793,7 +1839,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     }
 #undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());
-    return DASP_OK;
+    return finish_overlap();
 }
 
 } // namespace dasp
