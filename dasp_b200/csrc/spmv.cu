@@ -1631,6 +1631,9 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // other - the column-blocked kernel on a side stream forked from the caller's, limited to `overlap` CTAs per SM by
     // its shared-memory request so that CTAs of the fused kernel fit next to them, the long-row accumulators turned into y
     // by a small launch after the join.  Not with the short-band kernel (192 KB of shared memory per SM).
+    // Measured on C3 (profiles/r02/README.md section 4): 0.586 ms serial, 0.576 / 0.680 / 0.980 ms with 3 / 2 / 1 CTAs per SM left to
+    // the column-blocked kernel - both launches want the register file, and lcb_kernel loses more from fewer bytes in flight than
+    // the overlap gains.  Off unless DASP_LCB_OVERLAP is set.
     static const int overlap_env = getenv("DASP_LCB_OVERLAP") ? atoi(getenv("DASP_LCB_OVERLAP")) : 0;
     const bool sb_would_run = on_short && sb_selected(h) && ((uintptr_t)d_x & 15) == 0;
     const int overlap = (use_lcb && on_long && !sb_would_run && (on_med || on_short)) ? overlap_env : 0;
