@@ -80,6 +80,7 @@ struct SpmvArgs {
     // smq_k chunks of <= 8 groups; a medium CTA takes the next chunk of the SM it runs on (nullptr: CTA index = chunk)
     int *smq_cnt;
     int smq_n, smq_k;
+    int keep_compact; // small-matrix kernels read the compact column indices (chosen per launch, see medium_rows)
     const int *short_map;             // locality order of the short CTAs: category << 28 | CTA inside it (nullptr: off)
     int row_long, row_block, blocknum;
     // short
@@ -489,7 +490,7 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
 // medium rows (row blocks)
 
 // LEAN (with KEEP): the register-lean loop of the large matrices with the L2 policy and the dependent-launch wait of the small ones
-template <typename T, bool MMA, bool KEEP, bool LEAN = false>
+template <typename T, bool MMA, bool KEEP, bool LEAN = false, int PB = 0>
 __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWin<T> *win = nullptr)
 {
     const StreamPol pol = make_stream_policy<KEEP>();
@@ -669,55 +670,85 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
             // entries of the irregular tail travel with the first batch.  FMA order = CSR order in both paths.
             // measured on C1/C2 (profiles/r01/README.md): FP64 10.6/10.7/12.1/14.3 us for B = 1/2/3/4, FP16 (blocks are
             // multiples of 4 tiles) 10.2/9.9/10.2/9.2 us
-            constexpr int B = sizeof(T) == 8 ? 2 : 4;
-            T va[B][4], vb[B][4];
-            int ca[B][4], cb[B][4];
-            auto load = [&](T(&v)[B][4], int(&c)[B][4], int k) {
+            constexpr int B = PB > 0 ? PB : (sizeof(T) == 8 ? 2 : 4);
+            // The column indices of a batch travel as reg_cid (32 bits) or in the compact form (one 64-bit load of four 16-bit
+            // offsets + the tile base): 2 instead of 4 index bytes per entry, decoded when the gathers are issued.  The compact
+            // form wins where the index bytes dominate the stream (FP16: 6.4 vs 7.2 us on the C2 stand-in) and is chosen per
+            // launch (a.keep_compact); a warp with a wide block reads reg_cid.
+            auto pipe = [&](auto compact_c) {
+                constexpr bool CP = decltype(compact_c)::value;
+                constexpr int NI = CP ? 3 : 4; // index registers per tile: two packed words + base, or four columns
+                T va[B][4], vb[B][4];
+                int ca[B][NI], cb[B][NI];
+                auto load = [&](T(&v)[B][4], int(&c)[B][NI], int k) {
 #pragma unroll
-                for (int j = 0; j < B; j++) {
-                    // (latency-bound: the 32-bit reg_cid is read directly, the compact form only pays off when DRAM-bound)
-                    if (k + j < nt) { ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol); ld_stream4<KEEP>(pc + 32 * (k + j), c[j], pol); }
-                    else {
+                    for (int j = 0; j < B; j++) {
+                        if (k + j < nt) {
+                            ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol);
+                            if constexpr (CP) {
+                                asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;"
+                                             : "=r"(c[j][0]), "=r"(c[j][1]) : "l"(pd + 32 * (k + j)), "l"(pol.desc));
+                                c[j][2] = __ldg(pb + k + j);
+                            } else {
+                                int t4[4];
+                                ld_stream4<KEEP>(pc + 32 * (k + j), t4, pol);
 #pragma unroll
-                        for (int e = 0; e < 4; e++) { v[j][e] = T(0); c[j][e] = 0; }
+                                for (int e = 0; e < 4; e++) c[j][e] = t4[e];
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) v[j][e] = T(0);
+#pragma unroll
+                            for (int e = 0; e < NI; e++) c[j][e] = CP ? (e < 2 ? -1 : 0) : 0; // 0xFFFF offsets = column 0
+                        }
                     }
+                };
+                auto consume = [&](const T(&v)[B][4], const int(&c)[B][NI]) {
+                    A xv[B][4];
+#pragma unroll
+                    for (int j = 0; j < B; j++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            int col;
+                            if constexpr (CP) {
+                                const unsigned w = (unsigned)c[j][e >> 1];
+                                const unsigned h16 = (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+                                col = h16 == 0xFFFFu ? 0 : c[j][2] + (int)h16;
+                            } else col = c[j][e];
+                            xv[j][e] = gather(x, col, win);
+                        }
+#pragma unroll
+                    for (int j = 0; j < B; j++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
+                };
+                load(va, ca, 0);
+                constexpr int IR = 2;
+                T wv[IR];
+                int wc[IR];
+#pragma unroll
+                for (int j = 0; j < IR; j++) {
+                    const bool ok = lo + j < hi;
+                    wv[j] = ok ? ld_stream1(iv + lo + j, pol) : T(0);
+                    wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
                 }
+                pdl_wait(); // streams of the first batch are in flight; x and y may belong to the previous kernel
+                window_ready();
+                for (int k = 0; k < nt; k += 2 * B) {
+                    load(vb, cb, k + B);
+                    consume(va, ca);
+                    load(va, ca, k + 2 * B);
+                    consume(vb, cb);
+                }
+                A xw[IR];
+#pragma unroll
+                for (int j = 0; j < IR; j++) xw[j] = gather(x, wc[j], win);
+#pragma unroll
+                for (int j = 0; j < IR; j++) acc += to_acc(wv[j]) * xw[j];
+                for (int i = lo + IR; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
             };
-            auto consume = [&](const T(&v)[B][4], const int(&c)[B][4]) {
-                A xv[B][4];
-#pragma unroll
-                for (int j = 0; j < B; j++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) xv[j][e] = gather(x, c[j][e], win);
-#pragma unroll
-                for (int j = 0; j < B; j++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
-            };
-            load(va, ca, 0);
-            constexpr int IR = 2;
-            T wv[IR];
-            int wc[IR];
-#pragma unroll
-            for (int j = 0; j < IR; j++) {
-                const bool ok = lo + j < hi;
-                wv[j] = ok ? ld_stream1(iv + lo + j, pol) : T(0);
-                wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
-            }
-            pdl_wait(); // streams of the first batch are in flight; x and y may belong to the previous kernel
-            window_ready();
-            for (int k = 0; k < nt; k += 2 * B) {
-                load(vb, cb, k + B);
-                consume(va, ca);
-                load(va, ca, k + 2 * B);
-                consume(vb, cb);
-            }
-            A xw[IR];
-#pragma unroll
-            for (int j = 0; j < IR; j++) xw[j] = gather(x, wc[j], win);
-#pragma unroll
-            for (int j = 0; j < IR; j++) acc += to_acc(wv[j]) * xw[j];
-            for (int i = lo + IR; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
+            if (a.keep_compact && compact) pipe(std::true_type{});
+            else pipe(std::false_type{});
         }
         if (g < a.row_block) store_y<T>(a, (long)a.row_long + g, acc);
         return;
@@ -980,6 +1011,8 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
         break;
     case 1:
         if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, w);
+        else if constexpr (MED == 3) medium_rows<T, false, KEEP, true>(a, w); // small matrices, register-lean loop
+        else if constexpr (MED == 4) medium_rows<T, false, KEEP, false, 1>(a, w); // A/B aid: pipelined loop, one tile per batch, 4 CTAs per SM
         else medium_rows<T, MED == 1, KEEP>(a, w);
         break;
     case 2: short_singles<T, KEEP>(a, w); break;
@@ -995,7 +1028,7 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
 // compiled for 7 CTAs per SM (<= 72 registers, 4144 warp slots) so that every warp of an L2-resident matrix is resident at once: a 121 k-row
 // matrix is 3788 warps, the 256-thread / 84-register form holds 3552 and leaves a 60 %-empty second wave.
 template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false, int NT = CTA>
-__global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
+__global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : (MED >= 3 ? 4 : 1)) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
@@ -1013,7 +1046,7 @@ __global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : 1) : MED_MINB) spm
         }
     }
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
-    if constexpr (KEEP) { if (!(cat == 1 && MED == 0)) pdl_wait(); }
+    if constexpr (KEEP) { if (!(cat == 1 && (MED == 0 || MED == 3 || MED == 4))) pdl_wait(); }
     run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * (NT / 32) + warp, dyn_smem);
 }
 
@@ -1740,6 +1773,13 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // measured (profiles/r02): the 128-thread / 7-CTA form is SLOWER on C1 / C2 (17.9 vs 9.3 us, 12.2 vs 7.2 us): kept as an A/B aid
     static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 256;
     const bool narrow = keep && keep_shape == 128;
+    static const int keep_compact_env = getenv("DASP_KEEP_COMPACT") ? atoi(getenv("DASP_KEEP_COMPACT")) : -1; // A/B aid
+    a.keep_compact = keep_compact_env >= 0 ? keep_compact_env : 0;
+    // Small matrices through the register-lean medium loop (64 registers, 4 CTAs per SM: the whole matrix is one wave).
+    // Measured on the cop20k_A stand-in (profiles/r02/README.md section 3): FP16 6.4 vs 7.0 us -> chosen for FP16; FP64 11.4 vs 9.0 us
+    // (its 4-tile batches need 88 bytes of spills at 64 registers) -> the pipelined loop stays.  DASP_KEEP_LEAN=0/1 overrides.
+    static const int keep_lean_env = getenv("DASP_KEEP_LEAN") ? atoi(getenv("DASP_KEEP_LEAN")) : -1;
+    const bool keep_lean = keep_lean_env >= 0 ? keep_lean_env != 0 : f16;
     const int nw = narrow ? 4 : WARPS;
     // small matrices: medium rows handed out by SM (smq_kernel, its own launch)
     static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
@@ -1825,7 +1865,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         else if (mma_long) { if (med == 1) DASP_LAUNCH(__half, 1, 1, false); else DASP_LAUNCH(__half, 0, 1, false); }
         else if (med == 1) DASP_LAUNCH(__half, 1, 0, false);
         else if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, 0, true); else DASP_LAUNCH(__half, 2, 0, false); }
-        else { if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
+        else { if (keep && keep_lean) DASP_LAUNCH(__half, 3, 0, true); else if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
     } else if (mma_short) { // DMMA short rows (comparison variant): with the plain or the DMMA long / medium paths
         if (med == 1 && mma_long) spmv_kernel<double, 1, 1, false, true><<<grid, CTA, 0, st>>>(a);
         else spmv_kernel<double, 0, 0, false, true><<<grid, CTA, 0, st>>>(a);
@@ -1838,7 +1878,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     } else {
         if (med == 2) { if (keep) DASP_LAUNCH(double, 2, 0, true); else DASP_LAUNCH(double, 2, 0, false); }
         else if (med == 1) DASP_LAUNCH(double, 1, 0, false);
-        else { if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
+        else { if (keep && keep_lean_env == 2) DASP_LAUNCH(double, 4, 0, true); else if (keep && keep_lean) DASP_LAUNCH(double, 3, 0, true); else if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
     }
 #undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());
