@@ -1013,6 +1013,7 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
         if constexpr (MED == 2) medium_rows_split<T, KEEP>(a, w);
         else if constexpr (MED == 3) medium_rows<T, false, KEEP, true>(a, w); // small matrices, register-lean loop
         else if constexpr (MED == 4) medium_rows<T, false, KEEP, false, 1>(a, w); // A/B aid: pipelined loop, one tile per batch, 4 CTAs per SM
+        else if constexpr (MED == 5) medium_rows<T, false, KEEP>(a, w);           // A/B aid: pipelined loop compiled for 3 CTAs per SM
         else medium_rows<T, MED == 1, KEEP>(a, w);
         break;
     case 2: short_singles<T, KEEP>(a, w); break;
@@ -1028,7 +1029,7 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
 // compiled for 7 CTAs per SM (<= 72 registers, 4144 warp slots) so that every warp of an L2-resident matrix is resident at once: a 121 k-row
 // matrix is 3788 warps, the 256-thread / 84-register form holds 3552 and leaves a 60 %-empty second wave.
 template <typename T, int MED, int LONGV, bool KEEP, bool SMMA = false, int NT = CTA>
-__global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : (MED >= 3 ? 4 : 1)) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
+__global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : (MED == 5 ? 3 : (MED >= 3 ? 4 : 1))) : MED_MINB) spmv_kernel(const __grid_constant__ SpmvArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // only the TMA long-row variant asks for any
     const int bid = blockIdx.x, warp = threadIdx.x >> 5;
@@ -1046,7 +1047,7 @@ __global__ void __launch_bounds__(NT, KEEP ? (NT == 128 ? 7 : (MED >= 3 ? 4 : 1)
         }
     }
     // the medium-row path (MED == 0) waits for the predecessor itself, after it has requested its first tiles
-    if constexpr (KEEP) { if (!(cat == 1 && (MED == 0 || MED == 3 || MED == 4))) pdl_wait(); }
+    if constexpr (KEEP) { if (!(cat == 1 && (MED == 0 || MED >= 3))) pdl_wait(); }
     run_category<T, MED, LONGV, KEEP, SMMA>(a, cat, (long)local * (NT / 32) + warp, dyn_smem);
 }
 
@@ -1878,7 +1879,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     } else {
         if (med == 2) { if (keep) DASP_LAUNCH(double, 2, 0, true); else DASP_LAUNCH(double, 2, 0, false); }
         else if (med == 1) DASP_LAUNCH(double, 1, 0, false);
-        else { if (keep && keep_lean_env == 2) DASP_LAUNCH(double, 4, 0, true); else if (keep && keep_lean) DASP_LAUNCH(double, 3, 0, true); else if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
+        else { if (keep && keep_lean_env == 3) DASP_LAUNCH(double, 5, 0, true); else if (keep && keep_lean_env == 2) DASP_LAUNCH(double, 4, 0, true); else if (keep && keep_lean) DASP_LAUNCH(double, 3, 0, true); else if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
     }
 #undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());
