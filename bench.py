@@ -285,6 +285,51 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 
+def bind_host_memory_to_gpu_node(local):
+    """Multi-GPU end-to-end runs move every rank's x and y over its own PCIe link, but the pinned host buffers of all ranks
+    come from whatever NUMA node the process happens to run on: prefer the node the GPU hangs off (sysfs numa_node of its PCI
+    device) for this process's allocations - set_mempolicy(MPOL_PREFERRED) - and, where the cgroup allows it, run on that
+    node's cores.  Best effort, reported in the bench line; never fatal."""
+    info = {"gpu_numa_node": None, "mempolicy_preferred": False, "cpu_affinity": False}
+    try:
+        import ctypes
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86-64
+        if libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64)) == 0:
+            info["mempolicy_preferred"] = True
+        try:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0) & cpus
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpu_affinity"] = True
+        except OSError:
+            pass
+    except Exception as e:  # no sysfs / no permission / not Linux x86-64: leave the defaults
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -302,6 +347,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    numa = bind_host_memory_to_gpu_node(local) if (world > 1 and not os.environ.get("DASP_BENCH_NO_NUMA")) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dasp_b200.load()
@@ -514,6 +560,8 @@ def run_ours(args):
                        "launches_per_spmv": h.launches_per_spmv()},
         "parity_check_rel_l2": chk,
     }
+    if numa is not None:
+        line["e2e"]["host_numa_binding_rank0"] = numa
     if breakdown:
         line["breakdown"] = breakdown
     if iterated is not None:
