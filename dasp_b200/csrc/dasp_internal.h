@@ -152,6 +152,12 @@ struct Layout {
     int lcb_nctas = 0;                      // CTAs of the LCB kernel (LCB_PART entries each, never across blocks)
     void *lcb_val = nullptr;                // [lcb_live]
     unsigned *lcb_idx = nullptr;            // [lcb_live] long-row index << 16 | column - block * width (row_long <= 65535)
+    // FP64: the same indices in 16 bits (what the kernel streams): 13 bits of column inside the block + 3 bits of row DELTA to
+    // the previous entry; every chunk of 1024 entries (what one warp walks in a row) restarts from lcb_chunk_row; a chunk
+    // with a delta > 7 is flagged in lcb_chunk_wide and read through lcb_idx
+    unsigned short *lcb_idx16 = nullptr;    // [lcb_live]
+    int *lcb_chunk_row = nullptr;           // [lcb_live / 1024]
+    unsigned char *lcb_chunk_wide = nullptr; // [lcb_live / 1024]
     int *lcb_blk_ptr = nullptr;             // [lcb_nblk + 1] first entry of each block (multiples of 4)
     int *lcb_cta_first = nullptr;           // [lcb_nblk + 1] first CTA of each block
     void *lcb_acc = nullptr;                // [LCB_COPIES][lcb_acc_stride] accumulators (double / float), zero between launches

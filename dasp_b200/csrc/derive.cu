@@ -389,13 +389,15 @@ __global__ void lcb_block_ptr(const int *__restrict__ sorted_key, int slots, int
     blk_ptr[b] = lo;
 }
 
-// padded entry count of every block: a multiple of 4 (one 256-bit value load + one 128-bit index load per lane)
+// padded entry count of every block: a multiple of 1024 (the chunk one warp walks: 8 steps of 128 entries, a lane loads four
+// values and four indices per step), so that chunks - and the parts of the CTAs, multiples of 1024 too - start on global
+// multiples of 1024 and a chunk's restart row is found at entry >> 10
 __global__ void lcb_padded_counts(const int *__restrict__ blk_ptr, int nblk, int part, int *__restrict__ pad_ptr,
                                   int *__restrict__ cta_first)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nblk) return;
-    const int cnt = b < nblk ? ((blk_ptr[b + 1] - blk_ptr[b] + 3) & ~3) : 0;
+    const int cnt = b < nblk ? ((blk_ptr[b + 1] - blk_ptr[b] + 1023) & ~1023) : 0;
     pad_ptr[b] = cnt;
     cta_first[b] = (cnt + part - 1) / part;
 }
@@ -419,6 +421,21 @@ __global__ void lcb_gather(const T *__restrict__ long_val, const int *__restrict
     const unsigned row = (unsigned)warp_row[p / longw];
     if (j < cnt) { val[i] = long_val[p]; idx[i] = (row << 16) | (unsigned)(long_cid[p] & bw_mask); }
     else { val[i] = T(0); idx[i] = row << 16; }
+}
+
+// 16-bit form of the packed indices (FP64 blocks are 8192 columns wide: 13 bits): column | row delta << 13, restart row per
+// chunk of 1024 entries, chunks with a delta > 7 flagged wide
+__global__ void lcb_encode16(const unsigned *__restrict__ idx, int total, unsigned short *__restrict__ idx16,
+                             int *__restrict__ chunk_row, unsigned char *__restrict__ chunk_wide)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned e = idx[i], row = e >> 16;
+    unsigned delta = 0;
+    if (i & 1023) delta = row - (idx[i - 1] >> 16); // rows ascend inside a block, and blocks start on multiples of 1024
+    else chunk_row[i >> 10] = (int)row;
+    if (delta > 7) { chunk_wide[i >> 10] = 1; delta = 7; }
+    idx16[i] = (unsigned short)((e & 0x1FFFu) | (delta << 13));
 }
 
 template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
@@ -471,6 +488,19 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     if (total > 0)
         lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.k_long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
                                                            nblk, total, longw, (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_idx);
+    // FP64, DASP_LCB_IDX16=1 only: the 16-bit index stream.  Measured (profiles/r02/README.md section 4): the kernel then moves 10.4
+    // instead of 12.6 GB on C5 (DRAM 66 vs 78 %) and is NOT faster (2.07 vs 2.00 ms; C3 0.37 vs 0.33 ms with its many wide
+    // chunks): the row reconstruction's warp scan costs six more load/store-unit wavefronts per step in a kernel whose
+    // load/store unit is already 75 % busy.  Not built unless asked for.
+    static const int idx16_env = getenv("DASP_LCB_IDX16") ? atoi(getenv("DASP_LCB_IDX16")) : 0;
+    if (idx16_env && sizeof(T) == 8 && bw_log2 <= 13 && total > 0) {
+        const size_t nchunks = (size_t)total >> 10;
+        DASP_TRY(pool.alloc((void **)&L.lcb_idx16, sizeof(unsigned short) * (size_t)total));
+        DASP_TRY(pool.alloc((void **)&L.lcb_chunk_row, sizeof(int) * nchunks));
+        DASP_TRY(pool.alloc((void **)&L.lcb_chunk_wide, nchunks));
+        DASP_CUDA(cudaMemsetAsync(L.lcb_chunk_wide, 0, nchunks, st));
+        lcb_encode16<<<grid_for(total, 256), 256, 0, st>>>(L.lcb_idx, total, L.lcb_idx16, L.lcb_chunk_row, L.lcb_chunk_wide);
+    }
     DASP_CUDA(cudaGetLastError());
     DASP_CUDA(cudaStreamSynchronize(st)); // the scratch is released by the guard
     L.lcb_bw_log2 = bw_log2; L.lcb_nblk = nblk; L.lcb_live = total; L.lcb_nctas = tot[1];
@@ -807,6 +837,8 @@ int relabel_columns(dasp_handle *h, const int *d_new_index, int n_new, cudaStrea
         DASP_CUDA(cudaStreamSynchronize(st));
         pool.release(L.lcb_val); pool.release(L.lcb_idx); pool.release(L.lcb_blk_ptr); pool.release(L.lcb_cta_first);
         pool.release(L.lcb_acc); pool.release(L.lcb_done);
+        pool.release(L.lcb_idx16); pool.release(L.lcb_chunk_row); pool.release(L.lcb_chunk_wide);
+        L.lcb_idx16 = nullptr; L.lcb_chunk_row = nullptr; L.lcb_chunk_wide = nullptr;
         L.lcb_val = nullptr; L.lcb_idx = nullptr; L.lcb_blk_ptr = nullptr; L.lcb_cta_first = nullptr; L.lcb_acc = nullptr;
         L.lcb_done = nullptr; L.lcb_nctas = 0; L.lcb_live = 0;
     }

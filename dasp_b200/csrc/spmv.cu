@@ -94,6 +94,9 @@ struct SpmvArgs {
     // column-blocked long rows (LCB, derive.cu)
     const void *lcb_val;
     const unsigned *lcb_idx; // long row << 16 | column inside the block
+    const unsigned short *lcb_idx16; // FP64: column | row delta << 13 (nullptr: read lcb_idx)
+    const int *lcb_chunk_row;        //   restart row of every 1024-entry chunk
+    const unsigned char *lcb_chunk_wide; // 1: the chunk has a delta > 7 and is read through lcb_idx
     const int *lcb_blk_ptr, *lcb_cta_first;
     void *lcb_acc;
     unsigned *lcb_done;
@@ -1125,7 +1128,10 @@ template <typename A> __device__ __forceinline__ void red_add(A *p, A v) { atomi
 __device__ __forceinline__ void ld_lcb4(const double *p, double (&v)[4], const StreamPol &) { ld_stream4d<false>(p, v); }
 __device__ __forceinline__ void ld_lcb4(const __half *p, __half (&v)[4], const StreamPol &pol) { ld_stream4<false>(p, v, pol); }
 
-template <typename T>
+// IDX16 (FP64): the indices are streamed in the 16-bit form (derive.cu: lcb_encode16) - 10 instead of 12 bytes per entry, of a
+// kernel that moves 6.3 TB/s.  The rows of a step are rebuilt from the deltas with one warp scan; a warp walks whole chunks
+// of 1024 entries (8 steps), each of which restarts from its own row, and reads a chunk flagged wide through lcb_idx.
+template <typename T, bool IDX16>
 __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ SpmvArgs a)
 {
     using A = typename Acc<T>::type;
@@ -1174,29 +1180,60 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
     auto step_addr = [&](int s) { return ((s >> 3) * (8 * WARPS) + warp * 8 + (s & 7)); }; // s-th step of this warp
     if (step_addr(0) < nsteps_part) {
         T v0[4], v1[4], v2[4];
-        int k0[4], k1[4], k2[4];
+        int k0[4], k1[4], k2[4]; // IDX16: [0], [1] four packed 16-bit indices, [2] restart row of the chunk, [3] its wide flag
         bool ok0, ok1, ok2;
         // a lane past the end of the part re-reads the indices of the part's last four entries (rows stay ascending)
-        // and takes zeros as values
+        // and takes zeros as values (parts are multiples of 1024 entries: does not happen with IDX16)
         auto load = [&](T(&v)[4], int(&k)[4], bool &ok, int s) {
             const int t = step_addr(s);
             const int q = beg + 128 * t + 4 * lane;
             ok = q < end;
             const int qi = ok ? q : end - 4;
             if (t < nsteps_part) {
-                ld_stream4<false>(reinterpret_cast<const int *>(a.lcb_idx) + qi, k, pol);
+                if constexpr (IDX16) {
+                    asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;" : "=r"(k[0]), "=r"(k[1]) : "l"(a.lcb_idx16 + qi), "l"(pol.desc));
+                    const int chunk = (beg >> 10) + (t >> 3);
+                    k[2] = __ldg(a.lcb_chunk_row + chunk);
+                    k[3] = __ldg(a.lcb_chunk_wide + chunk);
+                } else ld_stream4<false>(reinterpret_cast<const int *>(a.lcb_idx) + qi, k, pol);
                 if (ok) ld_lcb4(val + q, v, pol);
             }
         };
         A lane_acc = 0;
         int cur = -1; // row the private accumulators belong to
-        auto consume = [&](const T(&v)[4], const int(&k)[4], bool ok) {
+        int prev_row = 0; // IDX16: row of the last entry of the warp's previous step
+        auto consume = [&](const T(&v)[4], const int(&k)[4], bool ok, int s) {
             A p[4];
             int r[4];
+            if constexpr (IDX16) {
+                const int t = step_addr(s);
+                if (k[3]) { // wide chunk (a row delta > 7 somewhere in it): the 32-bit indices of this step, read now
+                    int w[4];
+                    ld_stream4<false>(reinterpret_cast<const int *>(a.lcb_idx) + beg + 128 * t + 4 * lane, w, pol);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                r[j] = (int)((unsigned)(ok ? k[j] : k[3]) >> 16); // past the end: the row of the part's last entry
-                p[j] = ok ? to_acc(v[j]) * to_acc(xs[k[j] & 0xFFFF]) : A(0);
+                    for (int j = 0; j < 4; j++) { r[j] = (int)((unsigned)w[j] >> 16); p[j] = to_acc(v[j]) * to_acc(xs[w[j] & 0xFFFF]); }
+                } else {
+                    unsigned h[4] = {(unsigned)k[0] & 0xFFFFu, (unsigned)k[0] >> 16, (unsigned)k[1] & 0xFFFFu, (unsigned)k[1] >> 16};
+                    const int d0 = h[0] >> 13, d1 = h[1] >> 13, d2 = h[2] >> 13, d3 = h[3] >> 13;
+                    int incl = d0 + d1 + d2 + d3; // rows this lane advances by; inclusive scan over the lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const int start = ((t & 7) == 0) ? k[2] : prev_row; // a chunk restarts from its own row (its first delta is 0)
+                    r[0] = start + incl - (d1 + d2 + d3);
+                    r[1] = r[0] + d1; r[2] = r[1] + d2; r[3] = r[2] + d3;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) p[j] = to_acc(v[j]) * to_acc(xs[h[j] & 0x1FFFu]);
+                }
+                prev_row = __shfl_sync(0xffffffffu, r[3], 31);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    r[j] = (int)((unsigned)(ok ? k[j] : k[3]) >> 16); // past the end: the row of the part's last entry
+                    p[j] = ok ? to_acc(v[j]) * to_acc(xs[k[j] & 0xFFFF]) : A(0);
+                }
             }
             if (__all_sync(0xffffffffu, r[0] == cur && r[3] == cur)) { lane_acc += (p[0] + p[1]) + (p[2] + p[3]); return; }
             // Some row other than `cur` appears in this step.  Fold the lane's own entries: `first` = its leading run,
@@ -1232,13 +1269,13 @@ __global__ void __launch_bounds__(CTA, 3) lcb_kernel(const __grid_constant__ Spm
         __syncthreads(); // the tail elements written with plain stores
         for (int s = 0;; s += 3) {
             load(v2, k2, ok2, s + 2);
-            consume(v0, k0, ok0);
+            consume(v0, k0, ok0, s);
             if (step_addr(s + 1) >= nsteps_part) break;
             load(v0, k0, ok0, s + 3);
-            consume(v1, k1, ok1);
+            consume(v1, k1, ok1, s + 1);
             if (step_addr(s + 2) >= nsteps_part) break;
             load(v1, k1, ok1, s + 4);
-            consume(v2, k2, ok2);
+            consume(v2, k2, ok2, s + 2);
             if (step_addr(s + 3) >= nsteps_part) break;
         }
         if (cur >= 0) {
@@ -1652,8 +1689,9 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         a.lcb_cta_first = L.lcb_cta_first; a.lcb_acc = L.lcb_acc; a.lcb_done = L.lcb_done;
         a.lcb_bw_log2 = L.lcb_bw_log2; a.lcb_nblk = L.lcb_nblk; a.lcb_nctas = L.lcb_nctas; a.ncols = L.x_len;
         if (!h->lcb_attr_set) {
-            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DASP_CUDA(cudaFuncSetAttribute(lcb_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->lcb_attr_set = 1;
         }
     }
@@ -1688,8 +1726,10 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
             else if (overlap == 1) lcb_smem = 200 * 1024;
             joined_later = true;
         }
-        if (f16) lcb_kernel<__half><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
-        else lcb_kernel<double><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
+        a.lcb_idx16 = L.lcb_idx16; a.lcb_chunk_row = L.lcb_chunk_row; a.lcb_chunk_wide = L.lcb_chunk_wide; // built only with DASP_LCB_IDX16=1
+        if (f16) lcb_kernel<__half, false><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
+        else if (L.lcb_idx16) lcb_kernel<double, true><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
+        else lcb_kernel<double, false><<<L.lcb_nctas, CTA, lcb_smem, lcb_stream>>>(a);
         DASP_CUDA(cudaGetLastError());
         if (joined_later) {
             DASP_CUDA(cudaEventRecord(h->ev_join, h->side_stream));

@@ -47,6 +47,32 @@ def _wide_mixed():
     return len(rows), n, rowptr.astype(np.int32), colidx, val
 
 
+def _lcb_row_deltas():
+    """Long rows for the column-blocked kernel's 16-bit index stream: 260 long rows over 30 column blocks of 8192, row i
+    living mostly in blocks i % 13 and (i + 5) % 13 + 13, so that inside a block consecutive entries jump 13 rows (chunks
+    flagged wide, read through the 32-bit indices), plus 40 long rows spread over all columns (small deltas) and a few medium /
+    short rows."""
+    rng = np.random.default_rng(77)
+    n = 30 * 8192
+    rows = []
+    for i in range(260):
+        b0, b1 = i % 13, (i + 5) % 13 + 13
+        cols = np.concatenate([b0 * 8192 + rng.choice(8192, 180, replace=False), b1 * 8192 + rng.choice(8192, 150, replace=False)])
+        rows.append(np.sort(cols))
+    for i in range(40):
+        rows.append(np.sort(rng.choice(n, 300 + 7 * i, replace=False)))
+    for i in range(50):
+        rows.append(np.sort(rng.choice(n, int(rng.integers(1, 40)), replace=False)))
+    order = rng.permutation(len(rows))
+    rows = [rows[k] for k in order]
+    lens = np.array([len(r) for r in rows])
+    rowptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    colidx = np.concatenate(rows).astype(np.int32)
+    val = rng.uniform(-1, 1, len(colidx))
+    return len(rows), n, rowptr.astype(np.int32), colidx, val
+
+
 CASES = {
     # every category populated (fixture F1 of SURVEY.md Appendix A)
     "mixed_f1": lambda: M.mixed(),
@@ -74,6 +100,7 @@ CASES = {
     # column spans around the 16-bit limit of the compact index form: every tile wide / mixed / column 0 present
     "wide_span_all": lambda: _lens([40] * 200 + [7] * 30, n=300000, seed=21),
     "wide_span_mixed": lambda: _wide_mixed(),
+    "lcb_row_deltas": lambda: _lcb_row_deltas(),
     "rowloop_59989": lambda: _lens([5] * 59989 + [1, 2, 3], n=70000, seed=8, window=64),
     "rowloop_59990": lambda: _lens([5] * 59990 + [1, 2, 3], n=70000, seed=8, window=64),
     "rowloop_399999": lambda: _lens([6] * 399999, n=400000, seed=9, window=64),
