@@ -423,6 +423,90 @@ __global__ void lcb_gather(const T *__restrict__ long_val, const int *__restrict
     else { val[i] = T(0); idx[i] = row << 16; }
 }
 
+// Bank-aware order inside the runs (FP64).  lcb_kernel gathers x from shared memory with 64-bit loads; the hardware serves a
+// quarter warp (8 lanes x 8 bytes) per pass, and two of its lanes conflict when their columns are equal modulo 16.  Lane l of
+// a step owns entries 4l .. 4l + 3, so gather j of lanes 8g .. 8g + 7 reads the stride-4 subsequence {32g + 4i + j, i < 8} of an
+// aligned 32-entry window: with random columns that is 1.9 passes instead of 1 (measured: 130 M of 264 M shared-memory
+// wavefronts on C5 are conflicts, and the load/store unit is what bounds the kernel).  The order of the entries INSIDE a run
+// (same row, same block) is free - the kernel sums a run in any order - so every run (cut at multiples of 1024 entries) is
+// re-ordered here: entries ranked inside their bank, sorted by (rank, bank) - any 16 consecutive ones then sit in distinct
+// banks as long as the banks are evenly filled - and dealt to the run's positions window by window, column j by column j.
+// One CTA per 1024-entry chunk, in place (the chunk is staged in shared memory); runs shorter than 16 entries stay as they are.
+__global__ void __launch_bounds__(128) lcb_bank_order(double *__restrict__ val, unsigned *__restrict__ idx, int total)
+{
+    __shared__ double sv[1024];
+    __shared__ unsigned si[1024];
+    __shared__ unsigned short dest[1024], seg[1025];
+    __shared__ int cnt[4][16], nseg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long base = (long)blockIdx.x * 1024;
+    if (base >= total) return;
+    for (int e = tid; e < 1024; e += 128) { sv[e] = val[base + e]; si[e] = idx[base + e]; dest[e] = (unsigned short)e; }
+    __syncthreads();
+    if (warp == 0) { // list of run starts
+        int n = 0;
+        for (int k = 0; k < 32; k++) {
+            const int e = 32 * k + lane;
+            const bool head = e == 0 || (si[e] >> 16) != (si[e - 1] >> 16);
+            const unsigned m = __ballot_sync(0xffffffffu, head);
+            if (head) seg[n + __popc(m & ((1u << lane) - 1))] = (unsigned short)e;
+            n += __popc(m);
+        }
+        if (lane == 0) { seg[n] = 1024; nseg = n; }
+    }
+    __syncthreads();
+    for (int s = warp; s < nseg; s += 4) {
+        const int s0 = seg[s], s1 = seg[s + 1], len = s1 - s0;
+        if (len < 16) continue;
+        if (lane < 16) cnt[warp][lane] = 0;
+        __syncwarp();
+        for (int e = s0 + lane; e < s1; e += 32) atomicAdd(&cnt[warp][si[e] & 15], 1);
+        __syncwarp();
+        int run[16]; // entries of every bank seen so far (the same in every lane)
+#pragma unroll
+        for (int b = 0; b < 16; b++) run[b] = 0;
+        for (int e0 = s0; e0 < s1; e0 += 32) {
+            const int e = e0 + lane;
+            const bool on = e < s1;
+            const int b = on ? (int)(si[e] & 15) : 16;
+            int rank = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const unsigned m = __ballot_sync(0xffffffffu, b == k);
+                if (b == k) { rank = run[k] + __popc(m & ((1u << lane) - 1)); }
+                run[k] += __popc(m);
+            }
+            if (on) {
+                // position in the (rank, bank) order: everything of a smaller rank, and the lower banks of the same rank
+                int q = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int c = cnt[warp][k];
+                    q += min(c, rank) + ((k < b && c > rank) ? 1 : 0);
+                }
+                // the q-th position of the run, positions taken window by window (aligned 32 entries) and inside a window by
+                // (p % 4, p / 4): the entries of gather j of a quarter warp are then consecutive in the (rank, bank) order
+                int lo = s0, p = -1;
+                while (p < 0) {
+                    const int hi = min(s1, (lo & ~31) + 32), n = hi - lo;
+                    if (q < n) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int first = lo + ((j - lo) & 3); // first position >= lo with position % 4 == j
+                            const int cj = first < hi ? ((hi - 1 - first) >> 2) + 1 : 0;
+                            if (p < 0) { if (q < cj) p = first + 4 * q; else q -= cj; }
+                        }
+                    } else { q -= n; lo = hi; }
+                }
+                dest[e] = (unsigned short)p;
+            }
+        }
+        __syncwarp(); // every lane is done with cnt before the next run resets it
+    }
+    __syncthreads();
+    for (int e = tid; e < 1024; e += 128) { const int p = dest[e]; val[base + p] = sv[e]; idx[base + p] = si[e]; }
+}
+
 // 16-bit form of the packed indices (FP64 blocks are 8192 columns wide: 13 bits): column | row delta << 13, restart row per
 // chunk of 1024 entries, chunks with a delta > 7 flagged wide
 __global__ void lcb_encode16(const unsigned *__restrict__ idx, int total, unsigned short *__restrict__ idx16,
@@ -488,6 +572,12 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     if (total > 0)
         lcb_gather<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)L.long_val, L.k_long_cid, sidx, warp_row, blk_ptr, L.lcb_blk_ptr,
                                                            nblk, total, longw, (1 << bw_log2) - 1, (T *)L.lcb_val, L.lcb_idx);
+    if constexpr (sizeof(T) == 8) {
+        // Measured (profiles/r02/README.md section 4): bank conflicts 130 M -> 86 M wavefronts, 1.99 -> 1.90 ms under ncu, but no
+        // difference between back-to-back launches (2.446 vs 2.454 ms per C5 product), and the pass costs 80 ms on C3: opt-in only
+        static const int bank_env = getenv("DASP_LCB_BANK_ORDER") ? atoi(getenv("DASP_LCB_BANK_ORDER")) : 0;
+        if (bank_env && total > 0) lcb_bank_order<<<total >> 10, 128, 0, st>>>((double *)L.lcb_val, L.lcb_idx, total);
+    }
     // FP64, DASP_LCB_IDX16=1 only: the 16-bit index stream.  Measured (profiles/r02/README.md section 4): the kernel then moves 10.4
     // instead of 12.6 GB on C5 (DRAM 66 vs 78 %) and is NOT faster (2.07 vs 2.00 ms; C3 0.37 vs 0.33 ms with its many wide
     // chunks): the row reconstruction's warp scan costs six more load/store-unit wavefronts per step in a kernel whose
