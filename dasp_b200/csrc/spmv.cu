@@ -602,15 +602,29 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
         if constexpr (!KEEP || LEAN) {
             // Large matrices (bandwidth-bound): four tiles (4 x (256-bit values + 128-bit indices)) in flight per
             // lane, consumed as they arrive (40 registers, 6 CTAs per SM); the last batch is predicated.
+            // Small matrices (KEEP && LEAN): the first two entries of the irregular tail are requested with the first tiles
+            // (a tail of up to two entries then adds one round trip to the row's chain instead of four).
+            constexpr int IRP = (KEEP && LEAN) ? 2 : 0;
+            T wv[IRP > 0 ? IRP : 1];
+            int wc[IRP > 0 ? IRP : 1];
+            if constexpr (IRP > 0) {
+#pragma unroll
+                for (int j = 0; j < IRP; j++) {
+                    const bool ok = lo + j < hi;
+                    wv[j] = ok ? ld_stream1(iv + lo + j, pol) : T(0);
+                    wc[j] = ok ? ld_stream1(a.irreg_cid + lo + j, pol) : 0;
+                }
+            }
             if (compact) {
                 // compact indices: 8 bytes of 16-bit offsets + a broadcast 32-bit tile base per tile, decoded just
                 // before the gathers so that only the packed form is live while the loads are in flight
-                for (int k = 0; k < nt; k += MED_TB) {
-                    T v[MED_TB][4];
-                    unsigned d[MED_TB][2];
-                    int base[MED_TB];
+                constexpr int TB = (LEAN && PB > 0) ? PB : MED_TB; // tiles per batch
+                for (int k = 0; k < nt; k += TB) {
+                    T v[TB][4];
+                    unsigned d[TB][2];
+                    int base[TB];
 #pragma unroll
-                    for (int j = 0; j < MED_TB; j++) {
+                    for (int j = 0; j < TB; j++) {
                         if (k + j < nt) {
                             ld_stream4<KEEP>(pv + 32 * (k + j), v[j], pol);
                             asm volatile(DASP_LD_HINT ".v2.u32 {%0,%1}, [%2], %3;"
@@ -625,16 +639,16 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
                     }
                     if (k == 0) window_ready();
                     if constexpr (KEEP) { if (k == 0) pdl_wait(); } // x may be the previous product's y
-                    A xv[MED_TB][4];
+                    A xv[TB][4];
 #pragma unroll
-                    for (int j = 0; j < MED_TB; j++)
+                    for (int j = 0; j < TB; j++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const unsigned h16 = (e & 1) ? (d[j][e >> 1] >> 16) : (d[j][e >> 1] & 0xFFFFu);
                             xv[j][e] = gather(x, h16 == 0xFFFFu ? 0 : base[j] + (int)h16, win);
                         }
 #pragma unroll
-                    for (int j = 0; j < MED_TB; j++)
+                    for (int j = 0; j < TB; j++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) acc += to_acc(v[j][e]) * xv[j][e];
                 }
@@ -665,7 +679,14 @@ __device__ __forceinline__ void medium_rows(const SpmvArgs &a, long w, const XWi
             }
             window_ready(); // rows without a regular tile reach their first gather here
             if constexpr (KEEP) pdl_wait();
-            for (int i = lo; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
+            if constexpr (IRP > 0) {
+                A xw[IRP];
+#pragma unroll
+                for (int j = 0; j < IRP; j++) xw[j] = gather(x, wc[j], win);
+#pragma unroll
+                for (int j = 0; j < IRP; j++) acc += to_acc(wv[j]) * xw[j];
+            }
+            for (int i = lo + IRP; i < hi; i++) acc += to_acc(ld_stream1(iv + i, pol)) * gather(x, ld_stream1(a.irreg_cid + i, pol), win);
         } else {
             // Small, L2-resident matrices (latency-bound: one launch is a handful of dependent round trips): B
             // tiles per batch, two batches in flight, software pipelined by hand (the asm loads keep program order) so
@@ -1017,6 +1038,8 @@ __device__ __forceinline__ void run_category(const SpmvArgs &a, int cat, long w,
         else if constexpr (MED == 3) medium_rows<T, false, KEEP, true>(a, w); // small matrices, register-lean loop
         else if constexpr (MED == 4) medium_rows<T, false, KEEP, false, 1>(a, w); // A/B aid: pipelined loop, one tile per batch, 4 CTAs per SM
         else if constexpr (MED == 5) medium_rows<T, false, KEEP>(a, w);           // A/B aid: pipelined loop compiled for 3 CTAs per SM
+        else if constexpr (MED == 6) medium_rows<T, false, KEEP, true, 3>(a, w);  // A/B aid: register-lean loop, 3 tiles per batch
+        else if constexpr (MED == 7) medium_rows<T, false, KEEP, true, 2>(a, w);  // A/B aid: register-lean loop, 2 tiles per batch
         else medium_rows<T, MED == 1, KEEP>(a, w);
         break;
     case 2: short_singles<T, KEEP>(a, w); break;
@@ -1816,11 +1839,15 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     const bool narrow = keep && keep_shape == 128;
     static const int keep_compact_env = getenv("DASP_KEEP_COMPACT") ? atoi(getenv("DASP_KEEP_COMPACT")) : -1; // A/B aid
     a.keep_compact = keep_compact_env >= 0 ? keep_compact_env : 0;
-    // Small matrices through the register-lean medium loop (64 registers, 4 CTAs per SM: the whole matrix is one wave).
-    // Measured on the cop20k_A stand-in (profiles/r02/README.md section 3): FP16 6.4 vs 7.0 us -> chosen for FP16; FP64 11.4 vs 9.0 us
-    // (its 4-tile batches need 88 bytes of spills at 64 registers) -> the pipelined loop stays.  DASP_KEEP_LEAN=0/1 overrides.
+    // Small matrices go through the register-lean medium loop (64 registers, 4 CTAs per SM: the whole matrix is one wave) and
+    // walk their 32-row groups in locality order (below), so that the CTAs resident together gather from one neighbourhood of
+    // x and the L1 serves most gathers.  Measured on the cop20k_A stand-in (profiles/r02/README.md section 3), back to back:
+    //   FP64  pipelined loop 9.0 us | + order 9.2 | lean 11.4 | lean + order 7.4 (3 tiles per batch: 7.36, 4: 7.43, 2: 7.53)
+    //   FP16  pipelined loop 7.0 us | + order 7.1 | lean  6.4 | lean + order 4.65 (4 tiles per batch; 3: 5.0, 2: 5.4)
+    // DASP_KEEP_LEAN = 0 (pipelined loop) / 1, 6, 7 (lean, 4 / 3 / 2 tiles per batch) / 2, 3 (A/B shapes) and DASP_KEEP_ORDER = 0 / 1 override.
     static const int keep_lean_env = getenv("DASP_KEEP_LEAN") ? atoi(getenv("DASP_KEEP_LEAN")) : -1;
-    const bool keep_lean = keep_lean_env >= 0 ? keep_lean_env != 0 : f16;
+    const bool keep_lean = keep_lean_env != 0;
+    const int lean_shape = keep_lean_env > 0 ? keep_lean_env : (f16 ? 1 : 6);
     const int nw = narrow ? 4 : WARPS;
     // small matrices: medium rows handed out by SM (smq_kernel, its own launch)
     static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
@@ -1873,6 +1900,10 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
             c5 == L.short_ctas[3])
             a.short_map = L.short_map;
     }
+    // small matrices walk their medium groups in locality order too when they run the lean loop (see keep_lean above)
+    static const int keep_order_env = getenv("DASP_KEEP_ORDER") ? atoi(getenv("DASP_KEEP_ORDER")) : -1;
+    const bool keep_order = keep_order_env >= 0 ? keep_order_env != 0 : (keep_lean && (lean_shape == 1 || lean_shape >= 6));
+    if (keep && keep_order && med == 0 && on_med && a.items[1] > 0) a.med_order = L.med_order;
 
     // the kernels that use no shared memory ask for the whole unified array as L1 (x gathers live there), as the
     // reference does (src/dasp_f64.h:1280-1283)
@@ -1906,7 +1937,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         else if (mma_long) { if (med == 1) DASP_LAUNCH(__half, 1, 1, false); else DASP_LAUNCH(__half, 0, 1, false); }
         else if (med == 1) DASP_LAUNCH(__half, 1, 0, false);
         else if (med == 2) { if (keep) DASP_LAUNCH(__half, 2, 0, true); else DASP_LAUNCH(__half, 2, 0, false); }
-        else { if (keep && keep_lean) DASP_LAUNCH(__half, 3, 0, true); else if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
+        else { if (keep && keep_lean && lean_shape == 6) DASP_LAUNCH(__half, 6, 0, true); else if (keep && keep_lean && lean_shape == 7) DASP_LAUNCH(__half, 7, 0, true); else if (keep && keep_lean) DASP_LAUNCH(__half, 3, 0, true); else if (keep) DASP_LAUNCH(__half, 0, 0, true); else DASP_LAUNCH(__half, 0, 0, false); }
     } else if (mma_short) { // DMMA short rows (comparison variant): with the plain or the DMMA long / medium paths
         if (med == 1 && mma_long) spmv_kernel<double, 1, 1, false, true><<<grid, CTA, 0, st>>>(a);
         else spmv_kernel<double, 0, 0, false, true><<<grid, CTA, 0, st>>>(a);
@@ -1919,7 +1950,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     } else {
         if (med == 2) { if (keep) DASP_LAUNCH(double, 2, 0, true); else DASP_LAUNCH(double, 2, 0, false); }
         else if (med == 1) DASP_LAUNCH(double, 1, 0, false);
-        else { if (keep && keep_lean_env == 3) DASP_LAUNCH(double, 5, 0, true); else if (keep && keep_lean_env == 2) DASP_LAUNCH(double, 4, 0, true); else if (keep && keep_lean) DASP_LAUNCH(double, 3, 0, true); else if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
+        else { if (keep && keep_lean && lean_shape == 6) DASP_LAUNCH(double, 6, 0, true); else if (keep && keep_lean && lean_shape == 7) DASP_LAUNCH(double, 7, 0, true); else if (keep && lean_shape == 3) DASP_LAUNCH(double, 5, 0, true); else if (keep && lean_shape == 2) DASP_LAUNCH(double, 4, 0, true); else if (keep && keep_lean) DASP_LAUNCH(double, 3, 0, true); else if (keep) DASP_LAUNCH(double, 0, 0, true); else DASP_LAUNCH(double, 0, 0, false); }
     }
 #undef DASP_LAUNCH
     DASP_CUDA(cudaGetLastError());
