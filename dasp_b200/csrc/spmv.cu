@@ -1835,7 +1835,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // keep the streams at normal L2 priority only when the whole working set is well below the L2 capacity
     const bool keep = small && med != 1 && !mma_long && !tma_long && !mma_short;
     // measured (profiles/r02): the 128-thread / 7-CTA form is SLOWER on C1 / C2 (17.9 vs 9.3 us, 12.2 vs 7.2 us): kept as an A/B aid
-    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 256;
+    static const int keep_shape = getenv("DASP_KEEP_CTA") ? atoi(getenv("DASP_KEEP_CTA")) : 0; // 0: the measured choice per dtype
     const bool narrow = keep && keep_shape == 128;
     static const int keep_compact_env = getenv("DASP_KEEP_COMPACT") ? atoi(getenv("DASP_KEEP_COMPACT")) : -1; // A/B aid
     a.keep_compact = keep_compact_env >= 0 ? keep_compact_env : 0;
@@ -1848,7 +1848,10 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     static const int keep_lean_env = getenv("DASP_KEEP_LEAN") ? atoi(getenv("DASP_KEEP_LEAN")) : -1;
     const bool keep_lean = keep_lean_env != 0;
     const int lean_shape = keep_lean_env > 0 ? keep_lean_env : (f16 ? 1 : 6);
-    const int nw = narrow ? 4 : WARPS;
+    // FP64 lean loop in 224-thread CTAs (7 warps; 4 CTAs per SM leave 72 registers per thread instead of 64): 7.07 vs 7.19 us
+    // on the C1 stand-in; DASP_KEEP_CTA=256 is the A/B switch
+    const bool nt224 = keep && (keep_shape == 224 || keep_shape == 0) && !f16 && keep_lean && lean_shape == 6 && med == 0 && !mma_long && !tma_long && !mma_short;
+    const int nw = narrow ? 4 : (nt224 ? 7 : WARPS);
     // small matrices: medium rows handed out by SM (smq_kernel, its own launch)
     static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
     if (keep && use_smq && !narrow && med == 0 && a.items[1] > 0 && L.smq_cnt) {
@@ -1932,7 +1935,19 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         } else                                                                                                     \
             spmv_kernel<T, MED, LV, KEEP><<<grid, CTA, LV == 2 ? TMA_SMEM_BYTES : 0, st>>>(a);                     \
     } while (0)
-    if (f16) {
+    if (nt224) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (h->carved_narrow != (const void *)spmv_kernel<double, 6, 0, true, false, 224>) {
+            cudaFuncSetAttribute(spmv_kernel<double, 6, 0, true, false, 224>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            h->carved_narrow = (const void *)spmv_kernel<double, 6, 0, true, false, 224>;
+        }
+        DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<double, 6, 0, true, false, 224>, a));
+    } else if (f16) {
         if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
         else if (mma_long) { if (med == 1) DASP_LAUNCH(__half, 1, 1, false); else DASP_LAUNCH(__half, 0, 1, false); }
         else if (med == 1) DASP_LAUNCH(__half, 1, 0, false);
