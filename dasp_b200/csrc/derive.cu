@@ -535,6 +535,8 @@ template <typename T> int build_lcb_t(dasp_handle *h, cudaStream_t st)
     while ((sizeof(T) << (bw_log2 + 1)) <= (size_t)LCB_BYTES) bw_log2++; // 8192 doubles / 32768 halves
     const int nblk = L.x_len > 0 ? (int)((((int64_t)L.x_len - 1) >> bw_log2) + 1) : 1;
     int *warp_row = nullptr, *key = nullptr, *idx = nullptr, *skey = nullptr, *sidx = nullptr, *blk_ptr = nullptr;
+    // the sort's scratch in one allocation: four key / index arrays, the radix sort's two ping-pong buffers and histograms
+    tmp.reserve(sizeof(int) * (6 * (size_t)slots + (size_t)s.warp_number + (size_t)nblk + (size_t)slots / 4 + 65536) + (8u << 20));
     DASP_TRY(tmp.alloc((void **)&warp_row, sizeof(int) * (size_t)s.warp_number));
     DASP_TRY(tmp.alloc((void **)&key, sizeof(int) * (size_t)slots));
     DASP_TRY(tmp.alloc((void **)&idx, sizeof(int) * (size_t)slots));
