@@ -1842,15 +1842,17 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     // Small matrices go through the register-lean medium loop (64 registers, 4 CTAs per SM: the whole matrix is one wave) and
     // walk their 32-row groups in locality order (below), so that the CTAs resident together gather from one neighbourhood of
     // x and the L1 serves most gathers.  Measured on the cop20k_A stand-in (profiles/r02/README.md section 3), back to back:
-    //   FP64  pipelined loop 9.0 us | + order 9.2 | lean 11.4 | lean + order 7.4 (3 tiles per batch: 7.36, 4: 7.43, 2: 7.53)
+    //   FP64  pipelined loop 9.0 us | + order 9.2 | lean 11.4 | lean + order 7.4 (256-thread CTAs; 3 tiles per batch: 7.36, 4: 7.43, 2: 7.53)
     //   FP16  pipelined loop 7.0 us | + order 7.1 | lean  6.4 | lean + order 4.65 (4 tiles per batch; 3: 5.0, 2: 5.4)
     // DASP_KEEP_LEAN = 0 (pipelined loop) / 1, 6, 7 (lean, 4 / 3 / 2 tiles per batch) / 2, 3 (A/B shapes) and DASP_KEEP_ORDER = 0 / 1 override.
     static const int keep_lean_env = getenv("DASP_KEEP_LEAN") ? atoi(getenv("DASP_KEEP_LEAN")) : -1;
-    const bool keep_lean = keep_lean_env != 0;
-    const int lean_shape = keep_lean_env > 0 ? keep_lean_env : (f16 ? 1 : 6);
+    // (FP64 matrices whose layout order is already the local one - stencils: no med_order - keep the pipelined loop: 3.3 vs 3.5 us
+    // on a 40^3 stencil; FP16 prefers the lean loop there too, 3.4 vs 3.5 us)
+    const bool keep_lean = keep_lean_env >= 0 ? keep_lean_env != 0 : (f16 || L.med_order != nullptr);
+    const int lean_shape = keep_lean_env > 0 ? keep_lean_env : 1; // four tiles per batch (FP64 in 224-thread CTAs: 6.93 vs 7.07 us with three)
     // FP64 lean loop in 224-thread CTAs (7 warps; 4 CTAs per SM leave 72 registers per thread instead of 64): 7.07 vs 7.19 us
     // on the C1 stand-in; DASP_KEEP_CTA=256 is the A/B switch
-    const bool nt224 = keep && (keep_shape == 224 || keep_shape == 0) && !f16 && keep_lean && lean_shape == 6 && med == 0 && !mma_long && !tma_long && !mma_short;
+    const bool nt224 = keep && (keep_shape == 224 || keep_shape == 0) && !f16 && keep_lean && (lean_shape == 6 || lean_shape == 1) && med == 0 && !mma_long && !tma_long && !mma_short;
     const int nw = narrow ? 4 : (nt224 ? 7 : WARPS);
     // small matrices: medium rows handed out by SM (smq_kernel, its own launch)
     static const int use_smq = getenv("DASP_SMQ") ? atoi(getenv("DASP_SMQ")) : 0; // measured slower (profiles/r02/README.md §3): off unless DASP_SMQ=1
@@ -1942,11 +1944,19 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (h->carved_narrow != (const void *)spmv_kernel<double, 6, 0, true, false, 224>) {
-            cudaFuncSetAttribute(spmv_kernel<double, 6, 0, true, false, 224>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-            h->carved_narrow = (const void *)spmv_kernel<double, 6, 0, true, false, 224>;
+        if (lean_shape == 1) { // A/B aid: four tiles per batch
+            if (h->carved_narrow != (const void *)spmv_kernel<double, 3, 0, true, false, 224>) {
+                cudaFuncSetAttribute(spmv_kernel<double, 3, 0, true, false, 224>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+                h->carved_narrow = (const void *)spmv_kernel<double, 3, 0, true, false, 224>;
+            }
+            DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<double, 3, 0, true, false, 224>, a));
+        } else {
+            if (h->carved_narrow != (const void *)spmv_kernel<double, 6, 0, true, false, 224>) {
+                cudaFuncSetAttribute(spmv_kernel<double, 6, 0, true, false, 224>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+                h->carved_narrow = (const void *)spmv_kernel<double, 6, 0, true, false, 224>;
+            }
+            DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<double, 6, 0, true, false, 224>, a));
         }
-        DASP_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<double, 6, 0, true, false, 224>, a));
     } else if (f16) {
         if (tma_long) DASP_LAUNCH(__half, 0, 2, false);
         else if (mma_long) { if (med == 1) DASP_LAUNCH(__half, 1, 1, false); else DASP_LAUNCH(__half, 0, 1, false); }
