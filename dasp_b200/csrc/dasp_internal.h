@@ -103,6 +103,7 @@ struct Layout {
     int x_len = 0; // length of the x the kernels index (n, or the size of the relabelled index space)
     // ---- derived launch data of this implementation (not part of the reference layout) ----
     int n_long_units = 0;
+    int long_unit_warps = 32;       // reference warps per long-row work unit: LONG_UNIT_WARPS, fewer when the long part is small (derive)
     int *long_unit_row = nullptr;   // [n_long_units] long row of each unit (execution order)
     int *long_unit_chunk = nullptr; // [n_long_units] which chunk of that row
     int *long_unit_first = nullptr; // [row_long+1]  first unit of each long row
@@ -201,7 +202,7 @@ namespace dasp {
 constexpr int SPMV_CTA = 256;           // threads per CTA of the fused kernel (bandwidth-bound form)
 constexpr int SINGLES_PER_THREAD = 4;   // single-entry rows per thread
 constexpr int SHORT_TILES_PER_WARP = 4; // 8x4 tiles of a short segment per warp
-constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = 32 reference "warps" of 64 (f16: 256) slots
+constexpr int LONG_UNIT_WARPS = 32; // one long-row work unit = at most 32 reference "warps" of 64 (f16: 256) slots (Layout::long_unit_warps)
 #ifndef DASP_LCB_PART
 #define DASP_LCB_PART 32768
 #endif

@@ -17,12 +17,12 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline unsigned grid_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // work units per long row: one unit = LONG_UNIT_WARPS reference warps (src/dasp_f64.h:1006 defines the warp)
-__global__ void units_per_row(const int *__restrict__ long_rpt_new, int row_long, int *__restrict__ upr)
+__global__ void units_per_row(const int *__restrict__ long_rpt_new, int row_long, int unit_warps, int *__restrict__ upr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row_long) return;
     int w = long_rpt_new[i + 1] - long_rpt_new[i];
-    upr[i] = (w + LONG_UNIT_WARPS - 1) / LONG_UNIT_WARPS;
+    upr[i] = (w + unit_warps - 1) / unit_warps;
 }
 
 __global__ void __launch_bounds__(256) invert_order(const int *__restrict__ order, int m, int *__restrict__ inv)
@@ -786,7 +786,7 @@ int derive_indices(dasp_handle *h, cudaStream_t st, unsigned long long *lines)
     const int longw = h->dtype == DASP_F16 ? 256 : 64, esz = (int)L.esz;
     if (cl > 0 && L.n_long_units > 0)
         compress_long_cid<<<grid_for((long)L.n_long_units * 32, 256), 256, 0, st>>>(
-            L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.k_long_cid, L.n_long_units, longw, LONG_UNIT_WARPS, esz,
+            L.long_unit_row, L.long_unit_chunk, L.long_rpt_new, L.k_long_cid, L.n_long_units, longw, L.long_unit_warps, esz,
             L.long_cbase, L.long_cdelta, L.long_wide, lines);
     if (L.reg_compact_done) L.reg_compact_done = 0; // written by pack_reg from the same indices (dasp_create): nothing to do this once
     else if (blocknum > 0) {
@@ -819,7 +819,10 @@ int decide_long_variant(dasp_handle *h, cudaStream_t st, const unsigned long lon
         L.s.long_gather_lines = L.long_lines_avg;
         double thr = 9.0; // measured crossover (profiles/r02/README.md): 5.1 lines (C5 sorted) -> chunked wins 1.69 vs 1.83 ms; 12.5 (C3 sorted) -> column-blocked wins 0.339 vs 0.372 ms; 31.7 / 32 (spec generators) -> column-blocked wins by 1.9x / 8x
         if (const char *e = getenv("DASP_LCB_THRESHOLD")) thr = atof(e);
-        if (L.long_lines_avg > thr && s.row_long <= 65535 && s.nnz_long >= 4 * LCB_PART) {
+        // (the column-blocked kernel needs a couple of CTAs per SM of 32768 entries each to fill the machine: a small long part
+        // stays with the chunked kernel and its finer units: 20.5 us blocked on the 1.1 M-entry case above)
+        static const long lcb_min = getenv("DASP_LCB_MIN_NNZ") ? atol(getenv("DASP_LCB_MIN_NNZ")) : 2L * 148 * LCB_PART;
+        if (L.long_lines_avg > thr && s.row_long <= 65535 && s.nnz_long >= lcb_min) {
             DASP_TRY(build_lcb(h, st));
             h->lcb_auto = L.lcb_nctas > 0;
             L.s.long_blocked = h->lcb_auto;
@@ -965,7 +968,17 @@ int derive(dasp_handle *h, cudaStream_t st)
     DASP_CUDA(cudaMemsetAsync(lines, 0, sizeof(unsigned long long), st));
     L.n_long_units = 0;
     if (cl > 0) {
-        units_per_row<<<grid_for(cl, 256), 256, 0, st>>>(L.long_rpt_new, cl, L.long_unit_first);
+        // A unit is what ONE warp walks serially.  A long part too small to give every SM a few dozen units of 32 reference
+        // warps is cut finer (power of two), so that a small matrix with a handful of long rows is not one long dependent
+        // chain per row: 1.1 M long entries in 655 rows took 20 us in units of 2048 entries.
+        const int sms = h->sm_count > 0 ? h->sm_count : 148;
+        int uw = LONG_UNIT_WARPS;
+        while (uw > 1 && (long)s.warp_number / uw < 32L * sms) uw >>= 1;
+        if (getenv("DASP_LONG_UNIT_WARPS")) uw = atoi(getenv("DASP_LONG_UNIT_WARPS")); // A/B aid
+        if (uw < 1) uw = 1;
+        if (uw > LONG_UNIT_WARPS) uw = LONG_UNIT_WARPS;
+        L.long_unit_warps = uw;
+        units_per_row<<<grid_for(cl, 256), 256, 0, st>>>(L.long_rpt_new, cl, uw, L.long_unit_first);
         DASP_TRY(scan_inplace(tmp, L.long_unit_first, cl + 1, st));
         DASP_CUDA(cudaMemcpyAsync(&L.n_long_units, L.long_unit_first + cl, sizeof(int), cudaMemcpyDeviceToHost, st));
         DASP_CUDA(cudaStreamSynchronize(st));

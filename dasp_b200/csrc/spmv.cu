@@ -64,7 +64,7 @@ struct SpmvArgs {
     const unsigned char *long_wide;    //   per unit (execution order): 1 = read long_cid; nullptr = compression off
     void *partial;
     unsigned *done;
-    int n_units, longw;
+    int n_units, longw, unit_warps;
     // medium
     const void *reg_val;
     const int *reg_cid, *blockPtr, *irreg_rpt;
@@ -318,8 +318,8 @@ __device__ __forceinline__ void long_rows(const SpmvArgs &a, long w, unsigned ch
     const int row = __ldg(a.unit_row + u), chunk = __ldg(a.unit_chunk + u);
     const int first = __ldg(a.unit_first + row), nunits = __ldg(a.unit_first + row + 1) - first;
     const long row_beg = (long)__ldg(a.long_rpt_new + row) * a.longw, row_end = (long)__ldg(a.long_rpt_new + row + 1) * a.longw;
-    const long beg = row_beg + (long)chunk * LONG_UNIT_WARPS * a.longw;
-    const long end = min(beg + (long)LONG_UNIT_WARPS * a.longw, row_end);
+    const long beg = row_beg + (long)chunk * a.unit_warps * a.longw;
+    const long end = min(beg + (long)a.unit_warps * a.longw, row_end);
     const T *val = static_cast<const T *>(a.long_val);
     A acc = 0;
     if constexpr (MMA && sizeof(T) == 8) {
@@ -1678,7 +1678,7 @@ int launch_spmv(dasp_handle *h, const void *d_x, void *d_y, const int *scatter, 
     }
     a.long_val = L.long_val; a.long_cid = L.k_long_cid; a.long_rpt_new = L.long_rpt_new;
     a.unit_row = L.long_unit_row; a.unit_chunk = L.long_unit_chunk; a.unit_first = L.long_unit_first; a.partial = L.long_partial; a.done = L.long_done;
-    a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64;
+    a.n_units = L.n_long_units; a.longw = f16 ? 256 : 64; a.unit_warps = L.long_unit_warps;
     a.long_cbase = L.long_cbase; a.long_cdelta = L.long_cdelta; a.long_wide = h->index_compression ? L.long_wide : nullptr;
     a.reg_val = L.reg_val; a.reg_cid = L.k_reg_cid; a.blockPtr = L.blockPtr; a.irreg_rpt = L.irreg_rpt;
     a.irreg_val = L.irreg_val; a.irreg_cid = L.k_irreg_cid; a.has_irreg = L.med_has_irreg;
