@@ -824,7 +824,7 @@ def power_iteration_hybrid(args, spec, wname, cuts, rank, world, dev, local, x0,
     import torch.distributed as dist
 
     import dasp_b200
-    from dasp_b200 import synth
+    from dasp_b200 import partition, synth
 
     m = int(spec.m)
     r0, r1 = cuts[rank], cuts[rank + 1]
@@ -847,30 +847,16 @@ def power_iteration_hybrid(args, spec, wname, cuts, rank, world, dev, local, x0,
         dist.all_reduce(glong)
     glong = glong[:nl]
     # column pieces of ALL long rows that fall into this rank's slab [r0, r1)
-    pc, pv, plen = [], [], []
+    pieces = []
     for g in glong.tolist():
         _, gc, gv, _ = synth.generate(spec, g, g + 1, dev)
         keep = (gc >= r0) & (gc < r1)
-        pc.append(gc[keep])
-        pv.append(gv[keep])
-        plen.append(int(keep.sum().item()))
-    # local matrix: the slab's rows with the long rows emptied, then one row per long-row piece
-    row_of = torch.repeat_interleave(torch.arange(rows, device=dev), lens)
-    is_long_row = torch.zeros(rows, dtype=torch.bool, device=dev)
-    is_long_row[long_local] = True
-    keep = ~is_long_row[row_of]
-    del row_of
-    lens_local = torch.where(is_long_row, torch.zeros_like(lens), lens)
-    all_lens = torch.cat([lens_local, torch.tensor(plen, dtype=torch.int64, device=dev)])
-    rp_l = torch.zeros(rows + nl + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(all_lens, 0, out=rp_l[1:])
-    ci_l = torch.cat([ci[keep]] + pc)
-    v_l = torch.cat([v[keep]] + pv)
+        pieces.append((gc[keep], gv[keep]))
+    # local matrix: the slab's rows with the long rows emptied, then one row per long-row piece (dasp_b200/partition.py,
+    # the same code the two-rank gloo test runs on the CPU)
+    rp_l, ci_l, v_l, cmin, cmax = partition.hybrid_local_matrix(rp, ci, v, r0, r1, long_local, pieces)
     nnz_l = int(rp_l[-1].item())
-    cshort = ci[keep]
-    cmin = int(cshort.min().item()) if cshort.numel() else r0
-    cmax = int(cshort.max().item()) if cshort.numel() else r0
-    del keep, cshort, pc, pv, rp, ci, v
+    del pieces, rp, ci, v
     torch.cuda.empty_cache()
     h = dasp_b200.Dasp(dasp_b200.DASP_F64, rows + nl, m, rp_l.to(torch.int32), ci_l.to(torch.int32), v_l, device=local, nnz=nnz_l)
     del rp_l, ci_l, v_l
@@ -881,16 +867,7 @@ def power_iteration_hybrid(args, spec, wname, cuts, rank, world, dev, local, x0,
     if world > 1:
         dist.all_reduce(need)
     need = need.tolist()
-    sends, recvs = [], []  # (peer, lo, hi) in global indices
-    for q in range(world):
-        if q == rank:
-            continue
-        lo, hi = max(r0, need[q][0]), min(r1, need[q][1])  # what q needs from my slab
-        if lo < hi:
-            sends.append((q, lo, hi))
-        lo, hi = max(cuts[q], need[rank][0]), min(cuts[q + 1], need[rank][1])  # what I need from q's slab
-        if lo < hi:
-            recvs.append((q, lo, hi))
+    sends, recvs = partition.halo_plan(need, cuts, rank)  # (peer, lo, hi) in global indices
     x = torch.zeros(m, dtype=torch.float64, device=dev)
     y = torch.zeros(rows + nl, dtype=torch.float64, device=dev)
     red = torch.zeros(nl + 1, dtype=torch.float64, device=dev)
