@@ -1,7 +1,7 @@
 // spmv.cu — y = A*x on the DASP layout, hand-written for sm_100a.
 //
 // Replaces the reference kernels dasp_spmv2<rowloop> + longPart_sum (src/dasp_f64.h:53-484,
-// src/dasp_f16.h:106-590).  One fused launch; the block index selects the row category like the
+// src/dasp_f16.h:106-590).  One fused launch (plus the two below where AUTO picks them); the block index selects the row category like the
 // reference does (src/dasp_f64.h:90,145,281,296,357,424), but the geometry is this implementation's:
 //
 //   long    one warp per work unit (<= 32 reference warps = 2048/8192 slots of ONE row), 32-slot coalesced
@@ -10,10 +10,14 @@
 //           last unit to arrive (self-resetting counter) — no second launch (K1+K2 of SURVEY §8a).
 //           Alternatives behind dasp_set_variant: DMMA tiles, TMA bulk-copy ring.
 //   medium  one warp per 4 blocks of 8 rows; lane = (block, row).  CUDA-core variant: every lane walks
-//           the 8x4 tiles of its row with one 256-bit value load + one 128-bit index load per tile and
-//           keeps its own accumulator (no cross-lane traffic, same summation order as serial CSR); a
-//           latency-oriented pipelined form of the same loop for small, L2-resident matrices (KEEP).
-//           Alternatives: the reference's DMMA m8n8k4 formulation on the same tiles (K3), 4 lanes per row.
+//           the 8x4 tiles of its row with one 256-bit value load + one 64-bit load of four 16-bit column offsets
+//           per tile and keeps its own accumulator (no cross-lane traffic, same summation order as serial CSR),
+//           groups walked in locality order.  Small, L2-resident matrices (KEEP) run the same loop at 4 CTAs per
+//           SM - one wave - with programmatic dependent launch; a pipelined form of the loop (round 1) is kept.
+//           Alternatives: the reference's DMMA m8n8k4 / HMMA m16n8k16 formulation on the same tiles (K3), 4 lanes
+//           per row, x windows in shared memory (mb_kernel), SM-affine queues (smq_kernel).
+//   Separate launches for matrices whose gathers do not coalesce: lcb_kernel (long rows, column-blocked copy, x
+//   blocks staged in shared memory by TMA), sb_kernel (short rows by row band, x windows staged by TMA).
 //   short   1 / 1&3 / 3&4 / 2&2 segments read as flat coalesced streams (alignment-free: the FP64
 //           short segments start at slot short_row_1, which is not a multiple of 4) and folded with
 //           shuffles inside each 4-slot tile row (K4-K7).
